@@ -1,0 +1,372 @@
+// lbm_kernels.cuh -- sm_100a device code for the D2Q9-BGK per-timestep path.
+//
+// Replaces, in ONE pass per timestep, what the reference does in two OpenCL kernels plus a
+// host round trip (reference file:line):
+//   accelerate_flow  kernels.cl:7-42      -> epilogue of the previous step (or accelerate_row_kernel)
+//   propagate        kernels.cl:80-98     -> periodic pull, 128-bit loads + warp shuffles
+//   rebound          kernels.cl:100-107   -> register permutation, selected per cell
+//   collision        kernels.cl:109-196   -> f32-strict BGK relaxation (arithmetic contract below)
+//   av_velocity      kernels.cl:198 + d2q9-bgk.c:408-423 -> fused double-precision tree reduction
+//
+// Layout (DESIGN.md "Data layout"): SoA, 9 planes per buffer, two buffers (ping-pong).  A slab
+// of `rows` lattice rows is stored with one ghost row below (storage row 0) and one above
+// (storage row rows+1), so the y-periodic wrap and the multi-GPU halo are the same mechanism:
+// whoever computes a boundary row also stores the three populations its vertical neighbour will
+// pull into that neighbour's ghost row (which is this GPU's own ghost row when there is one GPU,
+// or a peer pointer over NVLink when there are several).
+//
+// Arithmetic contract ("f32-strict"; mirrored bit-for-bit by oracle/canon_impl.h VARIANT_B200):
+// every operation below is written as an explicit round-to-nearest intrinsic, so nvcc can neither
+// contract nor reassociate it.  State after any number of steps is bit-identical to the oracle.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace lbm {
+
+constexpr unsigned FULL_MASK = 0xffffffffu;
+constexpr int FLAG_OBSTACLE = 1;   // cell is blocked (d2q9-bgk.c:627)
+constexpr int FLAG_ACCEL    = 2;   // fluid cell of global row ny-2 (kernels.cl:21,29)
+
+struct StepArgs {
+  const float*   src;        // 9 planes, plane k at src + k*ps, storage row r at + r*nx
+  float*         dst;
+  const uint8_t* flags;      // per storage cell, same row indexing as a plane
+  long long      ps;         // plane stride (floats)
+  long long      nvec;       // rows * nxv work items
+  int            nx, rows, nxv;
+  float          omega, a1, a2;
+  int            fuse_accel; // apply the NEXT step's accelerate_flow to the values being stored
+  float*         ghost_lo[3];// row base receiving planes 4,7,8 of the first owned row
+  float*         ghost_hi[3];// row base receiving planes 2,5,6 of the last owned row
+  double*        partials;   // [gridDim.x] per-block sums of cell speeds for this step
+};
+
+// ---- vector access helpers ---------------------------------------------------------------
+template <int VEC> __device__ __forceinline__ void ld_vec(const float* p, float (&v)[VEC]);
+template <> __device__ __forceinline__ void ld_vec<1>(const float* p, float (&v)[1]) { v[0] = *p; }
+template <> __device__ __forceinline__ void ld_vec<2>(const float* p, float (&v)[2]) {
+  const float2 a = *reinterpret_cast<const float2*>(p); v[0] = a.x; v[1] = a.y;
+}
+template <> __device__ __forceinline__ void ld_vec<4>(const float* p, float (&v)[4]) {
+  const float4 a = *reinterpret_cast<const float4*>(p); v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+}
+template <int VEC> __device__ __forceinline__ void st_vec(float* p, const float (&v)[VEC]);
+template <> __device__ __forceinline__ void st_vec<1>(float* p, const float (&v)[1]) { *p = v[0]; }
+template <> __device__ __forceinline__ void st_vec<2>(float* p, const float (&v)[2]) {
+  *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
+}
+template <> __device__ __forceinline__ void st_vec<4>(float* p, const float (&v)[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+
+template <int VEC> __device__ __forceinline__ unsigned ld_flags(const uint8_t* p);
+template <> __device__ __forceinline__ unsigned ld_flags<1>(const uint8_t* p) { return *p; }
+template <> __device__ __forceinline__ unsigned ld_flags<2>(const uint8_t* p) {
+  return *reinterpret_cast<const uint16_t*>(p);
+}
+template <> __device__ __forceinline__ unsigned ld_flags<4>(const uint8_t* p) {
+  return *reinterpret_cast<const uint32_t*>(p);
+}
+
+// populations arriving from the west neighbour (speeds 1,5,8): cells x-1 .. x+VEC-2 of `row`
+template <int VEC>
+__device__ __forceinline__ void pull_from_west(const float* row, int x, int nx, bool lane_has_it,
+                                               float (&out)[VEC])
+{
+  float a[VEC];
+  ld_vec<VEC>(row + x, a);
+  float left = __shfl_up_sync(FULL_MASK, a[VEC - 1], 1);
+  if (!lane_has_it) left = row[x == 0 ? nx - 1 : x - 1];
+  out[0] = left;
+#pragma unroll
+  for (int i = 1; i < VEC; i++) out[i] = a[i - 1];
+}
+
+// populations arriving from the east neighbour (speeds 3,6,7): cells x+1 .. x+VEC of `row`
+template <int VEC>
+__device__ __forceinline__ void pull_from_east(const float* row, int x, int nx, bool lane_has_it,
+                                               float (&out)[VEC])
+{
+  float a[VEC];
+  ld_vec<VEC>(row + x, a);
+  float right = __shfl_down_sync(FULL_MASK, a[0], 1);
+  if (!lane_has_it) right = row[x + VEC == nx ? 0 : x + VEC];
+#pragma unroll
+  for (int i = 0; i < VEC - 1; i++) out[i] = a[i + 1];
+  out[VEC - 1] = right;
+}
+
+// ---- one cell: bounce-back or BGK relaxation, optional next-step acceleration --------------
+// t[] pulled populations in, post-step populations out; returns the speed (0 for obstacles).
+__device__ __forceinline__ float relax_cell(float (&t)[9], unsigned flag, float omega, float a1,
+                                            float a2, bool fuse_accel)
+{
+  constexpr float W0 = (float)(4.0 / 9.0);    // float roundings of the double quotients,
+  constexpr float W1 = (float)(1.0 / 9.0);    // as kernels.cl:58-61 has them
+  constexpr float W2 = (float)(1.0 / 36.0);
+
+  float rho = __fadd_rn(t[0], t[1]);
+  rho = __fadd_rn(rho, t[2]); rho = __fadd_rn(rho, t[3]); rho = __fadd_rn(rho, t[4]);
+  rho = __fadd_rn(rho, t[5]); rho = __fadd_rn(rho, t[6]); rho = __fadd_rn(rho, t[7]);
+  rho = __fadd_rn(rho, t[8]);
+  const float mx = __fsub_rn(__fadd_rn(__fadd_rn(t[1], t[5]), t[8]),
+                             __fadd_rn(__fadd_rn(t[3], t[6]), t[7]));
+  const float my = __fsub_rn(__fadd_rn(__fadd_rn(t[2], t[5]), t[6]),
+                             __fadd_rn(__fadd_rn(t[4], t[7]), t[8]));
+  const float ux = __fdiv_rn(mx, rho);
+  const float uy = __fdiv_rn(my, rho);
+  const float usq = __fmaf_rn(uy, uy, __fmul_rn(ux, ux));
+  const float b = __fmaf_rn(-1.5f, usq, 1.0f);
+  const float wr0 = __fmul_rn(W0, rho), wr1 = __fmul_rn(W1, rho), wr2 = __fmul_rn(W2, rho);
+  const float u5 = __fadd_rn(ux, uy), u6 = __fsub_rn(uy, ux);
+
+  float o[9];
+  o[0] = __fmaf_rn(omega, __fsub_rn(__fmul_rn(wr0, b), t[0]), t[0]);
+#define LBM_RELAX(k, u, wr)                                                          \
+  {                                                                                  \
+    const float p = __fmaf_rn((u), __fmaf_rn((u), 4.5f, 3.0f), b);                   \
+    o[k] = __fmaf_rn(omega, __fsub_rn(__fmul_rn((wr), p), t[k]), t[k]);              \
+  }
+  LBM_RELAX(1,  ux, wr1) LBM_RELAX(2,  uy, wr1) LBM_RELAX(3, -ux, wr1) LBM_RELAX(4, -uy, wr1)
+  LBM_RELAX(5,  u5, wr2) LBM_RELAX(6,  u6, wr2) LBM_RELAX(7, -u5, wr2) LBM_RELAX(8, -u6, wr2)
+#undef LBM_RELAX
+
+  // inflow acceleration of the NEXT step, applied to the just-relaxed values of row ny-2
+  // (bit-identical to running accelerate_flow as a separate pre-pass: kernels.cl:29-41)
+  if (fuse_accel && (flag & FLAG_ACCEL)) {
+    if (__fsub_rn(o[3], a1) > 0.0f && __fsub_rn(o[6], a2) > 0.0f && __fsub_rn(o[7], a2) > 0.0f) {
+      o[1] = __fadd_rn(o[1], a1); o[5] = __fadd_rn(o[5], a2); o[8] = __fadd_rn(o[8], a2);
+      o[3] = __fsub_rn(o[3], a1); o[6] = __fsub_rn(o[6], a2); o[7] = __fsub_rn(o[7], a2);
+    }
+  }
+
+  const bool obst = flag & FLAG_OBSTACLE;
+  // rebound: opposite directions of the pulled values, rest population kept.  A select, not a
+  // 0/1 multiply as in kernels.cl:179-196, so a zero-density obstacle cell cannot leak a NaN.
+  const float r1 = t[3], r2 = t[4], r3 = t[1], r4 = t[2], r5 = t[7], r6 = t[8], r7 = t[5], r8 = t[6];
+  t[0] = obst ? t[0] : o[0];
+  t[1] = obst ? r1 : o[1]; t[2] = obst ? r2 : o[2]; t[3] = obst ? r3 : o[3]; t[4] = obst ? r4 : o[4];
+  t[5] = obst ? r5 : o[5]; t[6] = obst ? r6 : o[6]; t[7] = obst ? r7 : o[7]; t[8] = obst ? r8 : o[8];
+  return obst ? 0.0f : __fsqrt_rn(usq);
+}
+
+// block-wide deterministic sum (fixed shuffle tree, then fixed order over warps)
+template <int TPB>
+__device__ __forceinline__ double block_sum(double v)
+{
+  __shared__ double warp_part[TPB / 32];
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(FULL_MASK, v, off);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) warp_part[warp] = v;
+  __syncthreads();
+  double s = 0.0;
+  if (warp == 0) {
+    s = lane < TPB / 32 ? warp_part[lane] : 0.0;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(FULL_MASK, s, off);
+  }
+  return s;   // valid in thread 0
+}
+
+// ---- the fused timestep --------------------------------------------------------------------
+// One thread = VEC consecutive cells of one row.  Grid = ceil(rows*nx/VEC / TPB) blocks.
+template <int VEC, int TPB>
+__global__ void __launch_bounds__(TPB)
+lbm_step_kernel(const __grid_constant__ StepArgs A)
+{
+  const unsigned gid = blockIdx.x * TPB + threadIdx.x;     // nvec < 2^31 is checked at create
+  const bool active = gid < (unsigned)A.nvec;
+  const unsigned item = active ? gid : (unsigned)A.nvec - 1u;   // idle tail threads shadow the last item
+  const int r = (int)(item / (unsigned)A.nxv) + 1;         // storage row (1..rows)
+  const int c = (int)(item - (unsigned)(r - 1) * (unsigned)A.nxv);
+  const int x = c * VEC;
+  const int lane = threadIdx.x & 31;
+  const bool west_in_warp = lane > 0 && c > 0;
+  const bool east_in_warp = lane < 31 && c < A.nxv - 1;
+
+  const long long row_mid = (long long)r * A.nx;
+  const long long row_lo = row_mid - A.nx, row_hi = row_mid + A.nx;
+  const float* s = A.src;
+  const long long ps = A.ps;
+
+  float f[9][VEC];
+  ld_vec<VEC>(s + row_mid + x, f[0]);
+  ld_vec<VEC>(s + 2 * ps + row_lo + x, f[2]);
+  ld_vec<VEC>(s + 4 * ps + row_hi + x, f[4]);
+  pull_from_west<VEC>(s + 1 * ps + row_mid, x, A.nx, west_in_warp, f[1]);
+  pull_from_west<VEC>(s + 5 * ps + row_lo,  x, A.nx, west_in_warp, f[5]);
+  pull_from_west<VEC>(s + 8 * ps + row_hi,  x, A.nx, west_in_warp, f[8]);
+  pull_from_east<VEC>(s + 3 * ps + row_mid, x, A.nx, east_in_warp, f[3]);
+  pull_from_east<VEC>(s + 6 * ps + row_lo,  x, A.nx, east_in_warp, f[6]);
+  pull_from_east<VEC>(s + 7 * ps + row_hi,  x, A.nx, east_in_warp, f[7]);
+  const unsigned flags = ld_flags<VEC>(A.flags + row_mid + x);
+
+  double speed_sum = 0.0;
+#pragma unroll
+  for (int j = 0; j < VEC; j++) {
+    float t[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) t[k] = f[k][j];
+    const float sp = relax_cell(t, (flags >> (8 * j)) & 0xffu, A.omega, A.a1, A.a2, A.fuse_accel != 0);
+    speed_sum += (double)sp;
+#pragma unroll
+    for (int k = 0; k < 9; k++) f[k][j] = t[k];
+  }
+
+  if (active) {
+    float* d = A.dst + row_mid + x;
+#pragma unroll
+    for (int k = 0; k < 9; k++) st_vec<VEC>(d + k * ps, f[k]);
+    if (r == 1) {            // my south neighbour pulls 4,7,8 from this row
+      st_vec<VEC>(A.ghost_lo[0] + x, f[4]);
+      st_vec<VEC>(A.ghost_lo[1] + x, f[7]);
+      st_vec<VEC>(A.ghost_lo[2] + x, f[8]);
+    }
+    if (r == A.rows) {       // my north neighbour pulls 2,5,6 from this row
+      st_vec<VEC>(A.ghost_hi[0] + x, f[2]);
+      st_vec<VEC>(A.ghost_hi[1] + x, f[5]);
+      st_vec<VEC>(A.ghost_hi[2] + x, f[6]);
+    }
+  } else {
+    speed_sum = 0.0;
+  }
+
+  const double total = block_sum<TPB>(speed_sum);
+  if (threadIdx.x == 0) A.partials[blockIdx.x] = total;
+}
+
+// ---- small kernels ---------------------------------------------------------------------------
+
+// stand-alone accelerate_flow (kernels.cl:7-42) on storage row `r` of a buffer; used for the first
+// step of a run (every later step gets it from the previous step's epilogue).  Also refreshes the
+// ghost copies if that row happens to be a slab boundary row.
+__global__ void accelerate_row_kernel(float* buf, const uint8_t* flags, long long ps, int nx, int r,
+                                      int rows, float a1, float a2, float* glo7, float* glo8,
+                                      float* ghi5, float* ghi6)
+{
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= nx) return;
+  const long long i = (long long)r * nx + x;
+  if (!(flags[i] & FLAG_ACCEL)) return;
+  float* f1 = buf + 1 * ps + i; float* f3 = buf + 3 * ps + i; float* f5 = buf + 5 * ps + i;
+  float* f6 = buf + 6 * ps + i; float* f7 = buf + 7 * ps + i; float* f8 = buf + 8 * ps + i;
+  if (__fsub_rn(*f3, a1) > 0.0f && __fsub_rn(*f6, a2) > 0.0f && __fsub_rn(*f7, a2) > 0.0f) {
+    *f1 = __fadd_rn(*f1, a1); *f5 = __fadd_rn(*f5, a2); *f8 = __fadd_rn(*f8, a2);
+    *f3 = __fsub_rn(*f3, a1); *f6 = __fsub_rn(*f6, a2); *f7 = __fsub_rn(*f7, a2);
+    if (r == 1)    { glo7[x] = *f7; glo8[x] = *f8; }
+    if (r == rows) { ghi5[x] = *f5; ghi6[x] = *f6; }
+  }
+}
+
+// copy the boundary rows of a buffer into the neighbours' ghost rows (after upload / init)
+__global__ void halo_push_kernel(const float* buf, long long ps, int nx, int rows,
+                                 float* lo4, float* lo7, float* lo8,
+                                 float* hi2, float* hi5, float* hi6)
+{
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= nx) return;
+  const long long first = (long long)nx + x, last = (long long)rows * nx + x;
+  lo4[x] = buf[4 * ps + first]; lo7[x] = buf[7 * ps + first]; lo8[x] = buf[8 * ps + first];
+  hi2[x] = buf[2 * ps + last];  hi5[x] = buf[5 * ps + last];  hi6[x] = buf[6 * ps + last];
+}
+
+// initial equilibrium fill on the device (d2q9-bgk.c:573-594), ghost rows included
+__global__ void init_equilibrium_kernel(float* buf, long long ps, long long cells, float w0,
+                                        float w1, float w2)
+{
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < cells; i += stride) {
+    buf[i] = w0;
+#pragma unroll
+    for (int k = 1; k <= 4; k++) buf[k * ps + i] = w1;
+#pragma unroll
+    for (int k = 5; k <= 8; k++) buf[k * ps + i] = w2;
+  }
+}
+
+// second stage of the average-velocity reduction: block s sums the nblk partials of step s in a
+// fixed order and writes the slab's speed total for that step (divided later by tot_cells).
+// `counter` holds the index of the first step of this chunk inside `totals`.
+__global__ void reduce_partials_kernel(const double* partials, int nblk, double* totals,
+                                       const long long* counter)
+{
+  __shared__ double sm[256];
+  const double* p = partials + (long long)blockIdx.x * nblk;
+  double v = 0.0;
+  for (int i = threadIdx.x; i < nblk; i += 256) v += p[i];
+  sm[threadIdx.x] = v;
+  __syncthreads();
+  for (int off = 128; off > 0; off >>= 1) {
+    if (threadIdx.x < off) sm[threadIdx.x] += sm[threadIdx.x + off];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) totals[*counter + blockIdx.x] = sm[0];
+}
+
+__global__ void advance_counter_kernel(long long* counter, int by) { *counter += by; }
+
+// av_velocity on a resident state (d2q9-bgk.c:426-475): per-block sums of cell speeds computed
+// from the stored populations (no streaming, no collision).  Feeds calc_reynolds (:815-820).
+template <int TPB>
+__global__ void __launch_bounds__(TPB)
+av_velocity_kernel(const float* buf, const uint8_t* flags, long long ps, int nx, int rows,
+                   double* partials)
+{
+  const long long n = (long long)rows * nx;
+  const long long stride = (long long)gridDim.x * TPB;
+  double acc = 0.0;
+  for (long long i = (long long)blockIdx.x * TPB + threadIdx.x; i < n; i += stride) {
+    const long long q = i + nx;                 // skip the lower ghost row
+    if (flags[q] & FLAG_OBSTACLE) continue;
+    float t[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) t[k] = buf[k * ps + q];
+    float rho = __fadd_rn(t[0], t[1]);
+#pragma unroll
+    for (int k = 2; k < 9; k++) rho = __fadd_rn(rho, t[k]);
+    const float mx = __fsub_rn(__fadd_rn(__fadd_rn(t[1], t[5]), t[8]),
+                               __fadd_rn(__fadd_rn(t[3], t[6]), t[7]));
+    const float my = __fsub_rn(__fadd_rn(__fadd_rn(t[2], t[5]), t[6]),
+                               __fadd_rn(__fadd_rn(t[4], t[7]), t[8]));
+    const float ux = __fdiv_rn(mx, rho), uy = __fdiv_rn(my, rho);
+    acc += (double)__fsqrt_rn(__fmaf_rn(uy, uy, __fmul_rn(ux, ux)));
+  }
+  const double total = block_sum<TPB>(acc);
+  if (threadIdx.x == 0) partials[blockIdx.x] = total;
+}
+
+// final-state fields of write_values (d2q9-bgk.c:857-897), same float expressions
+__global__ void macroscopic_kernel(const float* buf, const uint8_t* flags, long long ps, int nx,
+                                   int rows, float density, float* ux_out, float* uy_out,
+                                   float* u_out, float* p_out)
+{
+  constexpr float C_SQ = (float)(1.0 / 3.0);
+  const long long n = (long long)rows * nx;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const long long q = i + nx;
+    if (flags[q] & FLAG_OBSTACLE) {
+      ux_out[i] = 0.0f; uy_out[i] = 0.0f; u_out[i] = 0.0f;
+      p_out[i] = __fmul_rn(density, C_SQ);
+      continue;
+    }
+    float t[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) t[k] = buf[k * ps + q];
+    float rho = __fadd_rn(0.0f, t[0]);
+#pragma unroll
+    for (int k = 1; k < 9; k++) rho = __fadd_rn(rho, t[k]);
+    const float mx = __fsub_rn(__fadd_rn(__fadd_rn(t[1], t[5]), t[8]),
+                               __fadd_rn(__fadd_rn(t[3], t[6]), t[7]));
+    const float my = __fsub_rn(__fadd_rn(__fadd_rn(t[2], t[5]), t[6]),
+                               __fadd_rn(__fadd_rn(t[4], t[7]), t[8]));
+    const float ux = __fdiv_rn(mx, rho), uy = __fdiv_rn(my, rho);
+    ux_out[i] = ux; uy_out[i] = uy;
+    u_out[i] = __fsqrt_rn(__fadd_rn(__fmul_rn(ux, ux), __fmul_rn(uy, uy)));
+    p_out[i] = __fmul_rn(rho, C_SQ);
+  }
+}
+
+}  // namespace lbm
