@@ -216,3 +216,10 @@ def slab_rows(ny, world, rank):
 
 def device_count():
     return int(load().lbm_device_count())
+
+
+def comm_unique_id():
+    """128 bytes of an ncclUniqueId (rank 0 makes it, the caller distributes it)"""
+    buf = C.create_string_buffer(128)
+    _check(load().lbm_comm_unique_id(C.cast(buf, C.c_void_p)), "lbm_comm_unique_id")
+    return buf.raw

@@ -5,6 +5,7 @@ this module; nothing on the product path does.
 """
 import ctypes as C
 import os
+import sys
 
 import numpy as np
 
@@ -97,7 +98,19 @@ class Reference:
         if not os.path.isfile(REF_LIB):
             raise RuntimeError("oracle/_ref/libref_lbm.so not built (needs the reference sources)")
         self.lib = C.CDLL(REF_LIB)
-        rc = self.lib.ref_open(paramfile.encode(), obstaclefile.encode(), workdir.encode())
+        # the reference's initialise() prints its OpenCL device list to stdout: keep it out of
+        # the caller's stdout (bench.py must print exactly one JSON line)
+        sys.stdout.flush()
+        saved = os.dup(1)
+        devnull = os.open(os.devnull, os.O_WRONLY)
+        os.dup2(devnull, 1)
+        try:
+            rc = self.lib.ref_open(paramfile.encode(), obstaclefile.encode(), workdir.encode())
+            C.CDLL(None).fflush(None)
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
+            os.close(devnull)
         if rc != 0:
             raise RuntimeError("ref_open failed: %d" % rc)
         nx, ny, it, tc = C.c_int(), C.c_int(), C.c_int(), C.c_int()
