@@ -95,7 +95,7 @@ struct lbm_lattice {
   std::vector<Slab> slabs;     // slabs driven by this process
   int cur = 0;                 // buffer holding the current state
   int host_y0 = 0;             // first lattice row of the caller's host planes (rank mode: the slab's)
-  int vec = 4, tpb = 256, chunk = 128;
+  int vec = 4, tpb = 128, chunk = 128;
   bool use_graph = true;
   double last_ms = 0;
   long long last_launches = 0;
@@ -116,9 +116,9 @@ cudaError_t launch_step_t(const StepArgs& a, int nblk, cudaStream_t st)
 cudaError_t launch_step(int vec, int tpb, const StepArgs& a, int nblk, cudaStream_t st)
 {
 #define LBM_CASE(V, T) if (vec == V && tpb == T) return launch_step_t<V, T>(a, nblk, st);
-  LBM_CASE(4, 128) LBM_CASE(4, 256) LBM_CASE(4, 512)
-  LBM_CASE(2, 128) LBM_CASE(2, 256) LBM_CASE(2, 512)
-  LBM_CASE(1, 128) LBM_CASE(1, 256) LBM_CASE(1, 512)
+  LBM_CASE(4, 64) LBM_CASE(4, 128) LBM_CASE(4, 256) LBM_CASE(4, 512)
+  LBM_CASE(2, 64) LBM_CASE(2, 128) LBM_CASE(2, 256) LBM_CASE(2, 512)
+  LBM_CASE(1, 64) LBM_CASE(1, 128) LBM_CASE(1, 256) LBM_CASE(1, 512)
 #undef LBM_CASE
   return cudaErrorInvalidValue;
 }
@@ -353,8 +353,10 @@ int create_impl(lbm_lattice** out, const lbm_params* p, const int* obstacles, in
   const int want_vec = env_int("LBM_VEC", vec);
   if ((want_vec == 1 || want_vec == 2 || want_vec == 4) && nx % want_vec == 0) vec = want_vec;
   h->vec = vec;
-  const int want_tpb = env_int("LBM_TPB", 256);
-  h->tpb = (want_tpb == 128 || want_tpb == 512) ? want_tpb : 256;
+  // 128-thread blocks measured best on B200 (profiles/r1_sweep.md): 7 resident blocks per SM at
+  // 70 registers and a finer-grained tail than 256/512
+  const int want_tpb = env_int("LBM_TPB", 128);
+  h->tpb = (want_tpb == 64 || want_tpb == 256 || want_tpb == 512) ? want_tpb : 128;
   h->chunk = std::max(2, env_int("LBM_CHUNK", 128)) & ~1;
   h->use_graph = env_int("LBM_GRAPH", 1) != 0;
   const int pad = std::max(0, env_int("LBM_PLANE_PAD", 0));
