@@ -1,5 +1,6 @@
 // lbm_engine.cu -- host side of the C ABI in include/lbm_b200.h: owns the device memory, streams,
-// CUDA graphs and the slab decomposition, and launches the kernels of lbm_kernels.cuh.
+// CUDA graphs, the slab decomposition and the inter-GPU plumbing, and launches the kernels of
+// lbm_kernels.cuh.
 //
 // What it replaces in the reference (d2q9-bgk.c): the t_ocl object bundle (:35-67), its creation
 // (:642-780), upload (:159-201), the `for tt` loop with its buffer ping-pong (:203-234),
@@ -8,19 +9,25 @@
 //
 // Design notes
 //  * A lattice is a ring of row slabs, one per GPU.  Slab storage has a ghost row below and above;
-//    the step kernel stores boundary-row outputs straight into the neighbour's ghost rows (peer
-//    pointers over NVLink; its own ghost rows when the ring has one member).  Steps on different
-//    slabs are ordered only against their two neighbours (events), never against the host.
+//    the step kernel stores boundary-row outputs straight into the neighbour's ghost rows: its own
+//    ghost rows when the ring has one member, peer pointers over NVLink otherwise (direct peer
+//    access when one process drives all GPUs, CUDA-IPC mappings when there is one process per GPU).
+//    Steps on different slabs are ordered only against their two ring neighbours -- by stream
+//    events inside one process, by release/acquire counters in peer memory across processes --
+//    never against the host.  LBM_HALO=nccl switches the multi-process halo to ncclSend/ncclRecv.
 //  * Between API calls the resident state is always the reference's canonical post-step state.
 //    Inside lbm_run the inflow acceleration of step t+1 is folded into the store epilogue of step t;
 //    the first step of a run is preceded by a stand-alone accelerate kernel and the last step of a
 //    run does not pre-accelerate.
 //  * The average-velocity reduction never leaves the device during a run: per-block double sums per
-//    step, reduced per chunk of steps by a second kernel into a per-step totals array that is
-//    copied back once, after the last step.
+//    step, reduced per chunk of steps by a second kernel into a per-step totals array.  After the
+//    last step the per-slab totals are combined in slab order (all-gathered first when the slabs
+//    live in different processes), so the result does not depend on timing.
 //  * On one GPU whole chunks of steps are replayed from a CUDA graph to take the launch overhead
 //    out of small grids.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
 
 #include <algorithm>
 #include <cstdarg>
@@ -62,12 +69,81 @@ int env_int(const char* name, int dflt)
   return (v && *v) ? atoi(v) : dflt;
 }
 
+// ---- NCCL, bound at run time ------------------------------------------------------------------
+// dlopen by soname: inside a PyTorch process this resolves to the libnccl.so.2 torch already
+// loaded, in the plain C program to the system one.  Only the one-process-per-GPU mode needs it.
+struct NcclApi {
+  void* so = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
+                            cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+NcclApi* nccl_api()
+{
+  static NcclApi api;
+  static bool tried = false;
+  if (tried) return api.so ? &api : nullptr;
+  tried = true;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) {
+    api.so = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (api.so) break;
+  }
+  if (!api.so) return nullptr;
+#define BIND(field, sym)                                                       \
+  *(void**)(&api.field) = dlsym(api.so, sym);                                  \
+  if (!api.field) { api.so = nullptr; return nullptr; }
+  BIND(GetUniqueId, "ncclGetUniqueId") BIND(CommInitRank, "ncclCommInitRank")
+  BIND(CommDestroy, "ncclCommDestroy") BIND(AllReduce, "ncclAllReduce")
+  BIND(AllGather, "ncclAllGather") BIND(Send, "ncclSend") BIND(Recv, "ncclRecv")
+  BIND(GroupStart, "ncclGroupStart") BIND(GroupEnd, "ncclGroupEnd")
+  BIND(GetErrorString, "ncclGetErrorString")
+#undef BIND
+  return &api;
+}
+
+#define NK(call)                                                                              \
+  do {                                                                                        \
+    ncclResult_t r_ = (call);                                                                 \
+    if (r_ != ncclSuccess)                                                                    \
+      return fail("NCCL error during '%s' at %s:%d: %s", #call, __FILE__, __LINE__,           \
+                  nccl_api()->GetErrorString(r_));                                            \
+  } while (0)
+
+enum { HALO_P2P = 0, HALO_NCCL = 1 };
+
+// one-process-per-GPU plumbing of a slab
+struct Comm {
+  ncclComm_t nccl = nullptr;
+  int rank = 0, world = 1;
+  int halo = HALO_P2P;
+  void* peer_lo = nullptr;       // IPC mapping of the lower neighbour's slab allocation
+  void* peer_hi = nullptr;       // ... upper neighbour's (same mapping when world == 2)
+  unsigned* peer_lo_flag = nullptr;   // lower neighbour's "my upper neighbour has done N steps"
+  unsigned* peer_hi_flag = nullptr;   // upper neighbour's "my lower neighbour has done N steps"
+  unsigned steps_done = 0;       // steps completed since creation (all ranks advance together)
+  float* dummy_ghost = nullptr;  // NCCL halo: the kernel's ghost stores go nowhere useful
+  long long* scratch64 = nullptr;
+  bool ready = false;            // fully attached: destroy may run its closing barrier
+};
+
 struct Slab {
   int        device = 0;
   int        rank = 0;        // position in the ring
   int        y0 = 0, rows = 0;
   long long  ps = 0;          // plane stride (floats)
+  char*      base = nullptr;  // one allocation: buffer 0 | buffer 1 | sync words
   float*     buf[2] = {nullptr, nullptr};
+  unsigned*  sync = nullptr;  // [0] steps done by my lower neighbour, [1] by my upper, [2] timeout
   uint8_t*   flags = nullptr;
   double*    partials = nullptr;   // [chunk][nblk]
   double*    totals = nullptr;     // [totals_cap] per-step speed totals of this slab
@@ -85,6 +161,17 @@ struct Slab {
   int        accel_row = 0;        // storage row of global row ny-2
 };
 
+const int LO_PLANES[3] = {4, 7, 8};   // pulled by the row below (kernels.cl:94,97,98)
+const int HI_PLANES[3] = {2, 5, 6};   // pulled by the row above (kernels.cl:92,95,96)
+
+long long plane_stride(int rows, int nx, int pad)
+{
+  const long long cells = (long long)(rows + 2) * nx;
+  return ((cells + 31) / 32) * 32 + ((long long)pad / 32) * 32;
+}
+
+size_t slab_bytes(long long ps) { return sizeof(float) * 18 * (size_t)ps + 256; }
+
 }  // namespace
 
 struct lbm_lattice {
@@ -93,9 +180,10 @@ struct lbm_lattice {
   long long tot_cells = 0;
   int world = 1;               // slabs in the ring
   std::vector<Slab> slabs;     // slabs driven by this process
+  Comm* comm = nullptr;        // set in one-process-per-GPU mode with world > 1
   int cur = 0;                 // buffer holding the current state
   int host_y0 = 0;             // first lattice row of the caller's host planes (rank mode: the slab's)
-  int vec = 4, tpb = 128, chunk = 128;
+  int vec = 4, tpb = 128, chunk = 128, pad = 0;
   bool use_graph = true;
   double last_ms = 0;
   long long last_launches = 0;
@@ -158,16 +246,6 @@ int launch_accelerate(lbm_lattice* h, Slab& s, int cur)
   return 0;
 }
 
-int launch_halo_push(lbm_lattice* h, Slab& s, int cur)
-{
-  const int nx = h->p.nx;
-  lbm::halo_push_kernel<<<(nx + 255) / 256, 256, 0, s.stream>>>(
-      s.buf[cur], s.ps, nx, s.rows, s.ghost_lo[cur][0], s.ghost_lo[cur][1], s.ghost_lo[cur][2],
-      s.ghost_hi[cur][0], s.ghost_hi[cur][1], s.ghost_hi[cur][2]);
-  CK(cudaGetLastError());
-  return 0;
-}
-
 int sync_all(lbm_lattice* h)
 {
   for (auto& s : h->slabs) {
@@ -177,15 +255,58 @@ int sync_all(lbm_lattice* h)
   return 0;
 }
 
+// all ranks have reached this point and their streams are idle (multi-process mode only)
+int comm_barrier(lbm_lattice* h)
+{
+  if (!h->comm) return 0;
+  Slab& s = h->slabs[0];
+  NcclApi* n = nccl_api();
+  CK(cudaStreamSynchronize(s.stream));
+  NK(n->AllReduce(h->comm->scratch64, h->comm->scratch64, 1, ncclInt64, ncclSum, h->comm->nccl, s.stream));
+  CK(cudaStreamSynchronize(s.stream));
+  return 0;
+}
+
+// NCCL flavour of the halo: my first row's 4,7,8 go down, my last row's 2,5,6 go up, straight
+// from / into the plane rows of buffer `b` (each a contiguous run of nx floats)
+int nccl_halo_exchange(lbm_lattice* h, Slab& s, int b)
+{
+  NcclApi* n = nccl_api();
+  Comm* c = h->comm;
+  const int nx = h->p.nx;
+  const int lo = (c->rank + c->world - 1) % c->world, hi = (c->rank + 1) % c->world;
+  float* base = s.buf[b];
+  NK(n->GroupStart());
+  for (int i = 0; i < 3; i++) {
+    NK(n->Send(base + LO_PLANES[i] * s.ps + (long long)nx, nx, ncclFloat, lo, c->nccl, s.stream));
+    NK(n->Send(base + HI_PLANES[i] * s.ps + (long long)s.rows * nx, nx, ncclFloat, hi, c->nccl, s.stream));
+    NK(n->Recv(base + LO_PLANES[i] * s.ps + (long long)(s.rows + 1) * nx, nx, ncclFloat, hi, c->nccl, s.stream));
+    NK(n->Recv(base + HI_PLANES[i] * s.ps, nx, ncclFloat, lo, c->nccl, s.stream));
+  }
+  NK(n->GroupEnd());
+  return 0;
+}
+
 // after the resident state changed from outside (upload / init): fill every ghost row
 int refresh_ghosts(lbm_lattice* h)
 {
   if (sync_all(h)) return 1;
+  if (comm_barrier(h)) return 1;
+  const int nx = h->p.nx;
   for (auto& s : h->slabs) {
     CK(cudaSetDevice(s.device));
-    if (launch_halo_push(h, s, h->cur)) return 1;
+    if (h->comm && h->comm->halo == HALO_NCCL) {
+      if (nccl_halo_exchange(h, s, h->cur)) return 1;
+      continue;
+    }
+    const int c = h->cur;
+    lbm::halo_push_kernel<<<(nx + 255) / 256, 256, 0, s.stream>>>(
+        s.buf[c], s.ps, nx, s.rows, s.ghost_lo[c][0], s.ghost_lo[c][1], s.ghost_lo[c][2],
+        s.ghost_hi[c][0], s.ghost_hi[c][1], s.ghost_hi[c][2]);
+    CK(cudaGetLastError());
   }
-  return sync_all(h);
+  if (sync_all(h)) return 1;
+  return comm_barrier(h);
 }
 
 int ensure_totals(lbm_lattice* h, long long iters)
@@ -236,10 +357,13 @@ int run_impl(lbm_lattice* h, int iters, double* av_out)
   if (iters < 0) return fail("lbm_run: negative iteration count");
   if (iters == 0) return 0;
   const size_t nslab = h->slabs.size();
+  Comm* comm = h->comm;
   const long long totals_before = h->slabs[0].totals_cap;
   if (ensure_totals(h, iters)) return 1;
   if (h->slabs[0].totals_cap != totals_before)
     for (auto& s : h->slabs) drop_graphs(s);   // the captured reduce node holds the old pointer
+  // every rank is idle and out of any other API call before peers start writing ghost rows
+  if (comm_barrier(h)) return 1;
 
   for (auto& s : h->slabs) {
     CK(cudaSetDevice(s.device));
@@ -250,7 +374,7 @@ int run_impl(lbm_lattice* h, int iters, double* av_out)
 
   int remaining = iters;
   int cur = h->cur;
-  if (nslab == 1 && h->use_graph) {
+  if (nslab == 1 && !comm && h->use_graph) {
     Slab& s = h->slabs[0];
     while (remaining > h->chunk) {
       if (!s.graph[cur] && build_graph(h, s, cur)) return 1;
@@ -270,20 +394,33 @@ int run_impl(lbm_lattice* h, int iters, double* av_out)
       for (size_t k = 0; k < nslab; k++) {
         Slab& s = h->slabs[k];
         CK(cudaSetDevice(s.device));
-        if (nslab > 1) {
-          // my neighbours must have finished the previous step: their stores into my ghost rows
-          // are complete and they no longer read the ghost rows I am about to overwrite
-          if (step_no > 0) {
-            const Slab& lo = h->slabs[(k + nslab - 1) % nslab];
-            const Slab& hi = h->slabs[(k + 1) % nslab];
-            CK(cudaStreamWaitEvent(s.stream, lo.ev_step[(step_no - 1) & 1], 0));
-            CK(cudaStreamWaitEvent(s.stream, hi.ev_step[(step_no - 1) & 1], 0));
-          }
+        // my ring neighbours must have finished the previous step: their stores into my ghost
+        // rows are complete and they no longer read the ghost rows I am about to overwrite
+        if (nslab > 1 && step_no > 0) {
+          const Slab& lo = h->slabs[(k + nslab - 1) % nslab];
+          const Slab& hi = h->slabs[(k + 1) % nslab];
+          CK(cudaStreamWaitEvent(s.stream, lo.ev_step[(step_no - 1) & 1], 0));
+          CK(cudaStreamWaitEvent(s.stream, hi.ev_step[(step_no - 1) & 1], 0));
+        }
+        if (comm && comm->halo == HALO_P2P) {
+          lbm::wait_neighbours_kernel<<<1, 2, 0, s.stream>>>(s.sync, comm->steps_done, s.sync + 2);
+          CK(cudaGetLastError());
+          h->last_launches++;
         }
         const StepArgs a = make_args(h, s, cur, fuse, i);
         CK(launch_step(h->vec, h->tpb, a, s.nblk, s.stream));
         if (nslab > 1) CK(cudaEventRecord(s.ev_step[step_no & 1], s.stream));
+        if (comm && comm->halo == HALO_P2P) {
+          lbm::signal_neighbours_kernel<<<1, 2, 0, s.stream>>>(comm->peer_lo_flag, comm->peer_hi_flag,
+                                                               comm->steps_done + 1);
+          CK(cudaGetLastError());
+          h->last_launches++;
+        } else if (comm) {
+          if (nccl_halo_exchange(h, s, cur ^ 1)) return 1;
+          h->last_launches++;
+        }
       }
+      if (comm) comm->steps_done++;
       h->last_launches += (long long)nslab;
       cur ^= 1;
     }
@@ -313,145 +450,272 @@ int run_impl(lbm_lattice* h, int iters, double* av_out)
   }
   h->last_ms = ms_max;
 
-  if (av_out) {
-    std::vector<double> tmp((size_t)iters);
-    std::fill(av_out, av_out + iters, 0.0);
+  if (comm) {
+    unsigned timed_out = 0;
+    CK(cudaMemcpy(&timed_out, h->slabs[0].sync + 2, sizeof timed_out, cudaMemcpyDeviceToHost));
+    if (timed_out) return fail("lbm_run: timed out waiting for a neighbour GPU (rank %d)", comm->rank);
+  }
+
+  std::fill(av_out, av_out + iters, 0.0);
+  std::vector<double> tmp((size_t)iters);
+  if (!comm) {
     for (auto& s : h->slabs) {          // fixed slab order: the cross-GPU sum is deterministic
       CK(cudaSetDevice(s.device));
       CK(cudaMemcpy(tmp.data(), s.totals, sizeof(double) * iters, cudaMemcpyDeviceToHost));
       for (int t = 0; t < iters; t++) av_out[t] += tmp[t];
     }
-    const double inv = (double)h->tot_cells;
-    for (int t = 0; t < iters; t++) av_out[t] /= inv;
+  } else {
+    // all-gather every rank's per-step totals, then add them in rank order on the host
+    Slab& s = h->slabs[0];
+    double* gathered = nullptr;
+    CK(cudaMalloc(&gathered, sizeof(double) * (size_t)iters * comm->world));
+    NK(nccl_api()->AllGather(s.totals, gathered, (size_t)iters, ncclDouble, comm->nccl, s.stream));
+    CK(cudaStreamSynchronize(s.stream));
+    for (int r = 0; r < comm->world; r++) {
+      CK(cudaMemcpy(tmp.data(), gathered + (size_t)r * iters, sizeof(double) * iters, cudaMemcpyDeviceToHost));
+      for (int t = 0; t < iters; t++) av_out[t] += tmp[t];
+    }
+    CK(cudaFree(gathered));
   }
+  const double denom = (double)h->tot_cells;
+  for (int t = 0; t < iters; t++) av_out[t] /= denom;
   return 0;
 }
 
-int create_impl(lbm_lattice** out, const lbm_params* p, const int* obstacles, int first_device,
-                int nslab)
+void read_tuning(lbm_lattice* h)
+{
+  const int nx = h->p.nx;
+  int vec = (nx % 4 == 0) ? 4 : (nx % 2 == 0) ? 2 : 1;
+  const int want_vec = env_int("LBM_VEC", vec);
+  if ((want_vec == 1 || want_vec == 2 || want_vec == 4) && nx % want_vec == 0) vec = want_vec;
+  h->vec = vec;
+  // 128-thread blocks: best or within 1 % of best on B200 for both the HBM-streaming and the
+  // L2-resident regime (profiles/r1_tuning.md)
+  const int want_tpb = env_int("LBM_TPB", 128);
+  h->tpb = (want_tpb == 64 || want_tpb == 256 || want_tpb == 512) ? want_tpb : 128;
+  h->chunk = std::max(2, env_int("LBM_CHUNK", 128)) & ~1;
+  h->use_graph = env_int("LBM_GRAPH", 1) != 0;
+  h->pad = std::max(0, env_int("LBM_PLANE_PAD", 0));
+}
+
+// device objects of one slab; obstacles_rows points at the slab's first row
+int create_slab(lbm_lattice* h, Slab& s, const int* obstacles_rows, long long* fluid_cells)
+{
+  const int nx = h->p.nx, ny = h->p.ny;
+  const long long cells = (long long)(s.rows + 2) * nx;
+  s.ps = plane_stride(s.rows, nx, h->pad);
+  s.nvec = (long long)s.rows * (nx / h->vec);
+  if (s.nvec >= (1LL << 31)) return fail("lbm_create: slab too large for 32-bit work index");
+  s.nblk = (int)((s.nvec + h->tpb - 1) / h->tpb);
+  s.owns_accel_row = (ny - 2 >= s.y0 && ny - 2 < s.y0 + s.rows);
+  s.accel_row = ny - 2 - s.y0 + 1;
+
+  CK(cudaSetDevice(s.device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, s.device));
+  if (prop.major < 10)
+    return fail("device %d (%s) is not an sm_100-class GPU; this library is built for sm_100a only",
+                s.device, prop.name);
+  CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+  CK(cudaEventCreate(&s.ev_begin));
+  CK(cudaEventCreate(&s.ev_end));
+  CK(cudaEventCreateWithFlags(&s.ev_step[0], cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&s.ev_step[1], cudaEventDisableTiming));
+  CK(cudaMalloc(&s.base, slab_bytes(s.ps)));
+  CK(cudaMemset(s.base, 0, slab_bytes(s.ps)));
+  s.buf[0] = reinterpret_cast<float*>(s.base);
+  s.buf[1] = s.buf[0] + 9 * s.ps;
+  s.sync = reinterpret_cast<unsigned*>(s.buf[1] + 9 * s.ps);
+  CK(cudaMalloc(&s.flags, (size_t)cells));
+  CK(cudaMalloc(&s.partials, sizeof(double) * (size_t)h->chunk * s.nblk));
+  CK(cudaMalloc(&s.counter, sizeof(long long)));
+  CK(cudaMemset(s.counter, 0, sizeof(long long)));
+
+  // flags: bit 0 obstacle, bit 1 fluid cell of the accelerated row (global ny-2)
+  std::vector<uint8_t> fl((size_t)cells, 0);
+  long long fluid = 0;
+  for (int r = 0; r < s.rows; r++) {
+    const int gy = s.y0 + r;
+    const int* orow = obstacles_rows + (size_t)r * nx;
+    uint8_t* frow = fl.data() + (size_t)(r + 1) * nx;
+    for (int x = 0; x < nx; x++) {
+      const bool ob = orow[x] != 0;
+      frow[x] = (uint8_t)((ob ? lbm::FLAG_OBSTACLE : 0) | ((!ob && gy == ny - 2) ? lbm::FLAG_ACCEL : 0));
+      fluid += !ob;
+    }
+  }
+  *fluid_cells += fluid;
+  CK(cudaMemcpy(s.flags, fl.data(), (size_t)cells, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+// ghost destinations of slab `s` inside the allocations `lo_base` / `hi_base` of its ring
+// neighbours, whose geometry is (lo_rows, lo_ps) / hi_ps
+void wire_ghosts(Slab& s, int nx, char* lo_base, int lo_rows, long long lo_ps, char* hi_base,
+                 long long hi_ps)
+{
+  for (int b = 0; b < 2; b++) {
+    float* lo_buf = reinterpret_cast<float*>(lo_base) + (long long)b * 9 * lo_ps;
+    float* hi_buf = reinterpret_cast<float*>(hi_base) + (long long)b * 9 * hi_ps;
+    for (int i = 0; i < 3; i++) {
+      s.ghost_lo[b][i] = lo_buf + LO_PLANES[i] * lo_ps + (long long)(lo_rows + 1) * nx;
+      s.ghost_hi[b][i] = hi_buf + HI_PLANES[i] * hi_ps;
+    }
+  }
+}
+
+void set_config_string(lbm_lattice* h)
+{
+  char cfg[320];
+  const char* mode = h->comm ? (h->comm->halo == HALO_NCCL ? "ranks+nccl-sendrecv" : "ranks+ipc-peer-stores")
+                             : (h->slabs.size() > 1 ? "one-process+peer-stores" : "single-gpu");
+  snprintf(cfg, sizeof cfg, "vec=%d tpb=%d chunk=%d graph=%d slabs=%d halo=%s plane_stride=%lld",
+           h->vec, h->tpb, h->chunk, (int)(h->use_graph && h->world == 1), h->world, mode,
+           h->slabs[0].ps);
+  h->config = cfg;
+}
+
+int common_checks(lbm_lattice** out, const lbm_params* p, const int* obstacles)
 {
   if (!out || !p || !obstacles) return fail("lbm_create: null argument");
   *out = nullptr;
   if (p->nx < 1 || p->ny < 1) return fail("lbm_create: bad grid %d x %d", p->nx, p->ny);
   int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
+    cudaGetLastError();
     return fail("lbm_create: no CUDA device available (this library has no CPU fallback)");
-  if (nslab < 1 || first_device < 0 || first_device + nslab > ndev)
-    return fail("lbm_create: %d GPU(s) requested from device %d but %d visible", nslab, first_device, ndev);
-  if (nslab > 1 && p->ny / nslab < 3)
-    return fail("lbm_create: %d rows cannot be split into %d slabs of >= 3 rows", p->ny, nslab);
+  }
+  return 0;
+}
 
+lbm_lattice* new_lattice(const lbm_params* p, int world)
+{
   lbm_lattice* h = new lbm_lattice();
   h->p = *p;
   // kernels.cl:17-18: float product, double divide, rounded to float
   h->a1 = (float)((double)(p->density * p->accel) / 9.0);
   h->a2 = (float)((double)(p->density * p->accel) / 36.0);
-  h->world = nslab;
-  const int nx = p->nx, ny = p->ny;
+  h->world = world;
+  read_tuning(h);
+  return h;
+}
 
-  int vec = (nx % 4 == 0) ? 4 : (nx % 2 == 0) ? 2 : 1;
-  const int want_vec = env_int("LBM_VEC", vec);
-  if ((want_vec == 1 || want_vec == 2 || want_vec == 4) && nx % want_vec == 0) vec = want_vec;
-  h->vec = vec;
-  // 128-thread blocks measured best on B200 (profiles/r1_sweep.md): 7 resident blocks per SM at
-  // 70 registers and a finer-grained tail than 256/512
-  const int want_tpb = env_int("LBM_TPB", 128);
-  h->tpb = (want_tpb == 64 || want_tpb == 256 || want_tpb == 512) ? want_tpb : 128;
-  h->chunk = std::max(2, env_int("LBM_CHUNK", 128)) & ~1;
-  h->use_graph = env_int("LBM_GRAPH", 1) != 0;
-  const int pad = std::max(0, env_int("LBM_PLANE_PAD", 0));
+int create_impl(lbm_lattice** out, const lbm_params* p, const int* obstacles, int first_device,
+                int nslab)
+{
+  if (common_checks(out, p, obstacles)) return 1;
+  int ndev = 0;
+  cudaGetDeviceCount(&ndev);
+  if (nslab < 1 || first_device < 0 || first_device + nslab > ndev)
+    return fail("lbm_create: %d GPU(s) requested from device %d but %d visible", nslab, first_device, ndev);
+  if (nslab > 1 && p->ny / nslab < 3)
+    return fail("lbm_create: %d rows cannot be split into %d slabs of >= 3 rows", p->ny, nslab);
 
+  lbm_lattice* h = new_lattice(p, nslab);
+  const int nx = p->nx;
   h->slabs.resize(nslab);
-  auto bail = [&](int) { lbm_destroy(h); return 1; };
-
   for (int k = 0; k < nslab; k++) {
     Slab& s = h->slabs[k];
     s.device = first_device + k;
     s.rank = k;
-    lbm_slab_rows(ny, nslab, k, &s.y0, &s.rows);
-    const long long cells = (long long)(s.rows + 2) * nx;
-    s.ps = ((cells + 31) / 32) * 32 + ((long long)pad / 32) * 32;
-    s.nvec = (long long)s.rows * (nx / vec);
-    if (s.nvec >= (1LL << 31)) { fail("lbm_create: slab too large for 32-bit work index"); return bail(0); }
-    s.nblk = (int)((s.nvec + h->tpb - 1) / h->tpb);
-    s.owns_accel_row = (ny - 2 >= s.y0 && ny - 2 < s.y0 + s.rows);
-    s.accel_row = ny - 2 - s.y0 + 1;
-
-    if (cudaSetDevice(s.device) != cudaSuccess) { fail("cudaSetDevice(%d) failed", s.device); return bail(0); }
-    cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, s.device) != cudaSuccess || prop.major < 10) {
-      fail("device %d is not an sm_100-class GPU (this library is built for sm_100a only)", s.device);
-      return bail(0);
-    }
-#define CKB(call)                                                                             \
-  do {                                                                                        \
-    cudaError_t e_ = (call);                                                                  \
-    if (e_ != cudaSuccess) {                                                                  \
-      fail("CUDA error during '%s' at %s:%d: %s", #call, __FILE__, __LINE__,                  \
-           cudaGetErrorString(e_));                                                           \
-      return bail(0);                                                                         \
-    }                                                                                         \
-  } while (0)
-    CKB(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
-    CKB(cudaEventCreate(&s.ev_begin));
-    CKB(cudaEventCreate(&s.ev_end));
-    CKB(cudaEventCreateWithFlags(&s.ev_step[0], cudaEventDisableTiming));
-    CKB(cudaEventCreateWithFlags(&s.ev_step[1], cudaEventDisableTiming));
-    for (int b = 0; b < 2; b++) {
-      CKB(cudaMalloc(&s.buf[b], sizeof(float) * 9 * s.ps));
-      CKB(cudaMemset(s.buf[b], 0, sizeof(float) * 9 * s.ps));
-    }
-    CKB(cudaMalloc(&s.flags, (size_t)cells));
-    CKB(cudaMalloc(&s.partials, sizeof(double) * (size_t)h->chunk * s.nblk));
-    CKB(cudaMalloc(&s.counter, sizeof(long long)));
-    CKB(cudaMemset(s.counter, 0, sizeof(long long)));
-
-    // flags: bit 0 obstacle, bit 1 fluid cell of the accelerated row (global ny-2)
-    std::vector<uint8_t> fl((size_t)cells, 0);
-    for (int r = 0; r < s.rows; r++) {
-      const int gy = s.y0 + r;
-      const int* orow = obstacles + (size_t)gy * nx;
-      uint8_t* frow = fl.data() + (size_t)(r + 1) * nx;
-      for (int x = 0; x < nx; x++) {
-        const bool ob = orow[x] != 0;
-        frow[x] = (uint8_t)((ob ? lbm::FLAG_OBSTACLE : 0) | ((!ob && gy == ny - 2) ? lbm::FLAG_ACCEL : 0));
-        h->tot_cells += !ob;
-      }
-    }
-    CKB(cudaMemcpy(s.flags, fl.data(), (size_t)cells, cudaMemcpyHostToDevice));
+    lbm_slab_rows(p->ny, nslab, k, &s.y0, &s.rows);
+    if (create_slab(h, s, obstacles + (size_t)s.y0 * nx, &h->tot_cells)) { lbm_destroy(h); return 1; }
   }
-
-  // ring wiring: where each slab's boundary rows land
   for (int k = 0; k < nslab; k++) {
     Slab& s = h->slabs[k];
     Slab& lo = h->slabs[(k + nslab - 1) % nslab];
     Slab& hi = h->slabs[(k + 1) % nslab];
-    static const int lo_planes[3] = {4, 7, 8}, hi_planes[3] = {2, 5, 6};
-    for (int b = 0; b < 2; b++)
-      for (int i = 0; i < 3; i++) {
-        s.ghost_lo[b][i] = lo.buf[b] + lo_planes[i] * lo.ps + (long long)(lo.rows + 1) * nx;
-        s.ghost_hi[b][i] = hi.buf[b] + hi_planes[i] * hi.ps;
-      }
+    wire_ghosts(s, nx, lo.base, lo.rows, lo.ps, hi.base, hi.ps);
     if (nslab > 1) {
-      CKB(cudaSetDevice(s.device));
+      cudaSetDevice(s.device);
       for (const Slab* nb : {&lo, &hi}) {
         if (nb->device == s.device) continue;
         int can = 0;
-        CKB(cudaDeviceCanAccessPeer(&can, s.device, nb->device));
-        if (!can) { fail("GPU %d cannot access GPU %d peer memory", s.device, nb->device); return bail(0); }
+        cudaDeviceCanAccessPeer(&can, s.device, nb->device);
+        if (!can) {
+          fail("GPU %d cannot access GPU %d peer memory", s.device, nb->device);
+          lbm_destroy(h);
+          return 1;
+        }
         cudaError_t e = cudaDeviceEnablePeerAccess(nb->device, 0);
         if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
-        else if (e != cudaSuccess) { fail("cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e)); return bail(0); }
+        else if (e != cudaSuccess) {
+          fail("cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+          lbm_destroy(h);
+          return 1;
+        }
       }
     }
   }
-#undef CKB
-
-  char cfg[256];
-  snprintf(cfg, sizeof cfg, "vec=%d tpb=%d chunk=%d graph=%d slabs=%d plane_stride=%lld",
-           h->vec, h->tpb, h->chunk, (int)h->use_graph, nslab, h->slabs[0].ps);
-  h->config = cfg;
+  set_config_string(h);
   *out = h;
+  return 0;
+}
+
+// one process per GPU: NCCL communicator, global cell count, IPC mapping of the two neighbours
+int attach_comm(lbm_lattice* h, int rank, int world, const void* unique_id)
+{
+  NcclApi* n = nccl_api();
+  if (!n) return fail("lbm_create_rank: libnccl.so.2 could not be loaded (%s)", dlerror());
+  if (!unique_id) return fail("lbm_create_rank: world > 1 needs an ncclUniqueId");
+  Slab& s = h->slabs[0];
+  Comm* c = new Comm();
+  h->comm = c;
+  c->rank = rank;
+  c->world = world;
+  const char* halo = getenv("LBM_HALO");
+  c->halo = (halo && !strcmp(halo, "nccl")) ? HALO_NCCL : HALO_P2P;
+  ncclUniqueId id;
+  memcpy(&id, unique_id, sizeof id);
+  NK(n->CommInitRank(&c->nccl, world, id, rank));
+  CK(cudaMalloc(&c->scratch64, sizeof(long long) * 2));
+  CK(cudaMemset(c->scratch64, 0, sizeof(long long) * 2));
+
+  // global number of fluid cells (d2q9-bgk.c:146-152 counts them over the whole grid)
+  long long* d_cnt = c->scratch64 + 1;
+  CK(cudaMemcpy(d_cnt, &h->tot_cells, sizeof(long long), cudaMemcpyHostToDevice));
+  NK(n->AllReduce(d_cnt, d_cnt, 1, ncclInt64, ncclSum, c->nccl, s.stream));
+  CK(cudaStreamSynchronize(s.stream));
+  CK(cudaMemcpy(&h->tot_cells, d_cnt, sizeof(long long), cudaMemcpyDeviceToHost));
+
+  const int nx = h->p.nx;
+  const int lo = (rank + world - 1) % world, hi = (rank + 1) % world;
+  int lo_y0, lo_rows, hi_y0, hi_rows;
+  lbm_slab_rows(h->p.ny, world, lo, &lo_y0, &lo_rows);
+  lbm_slab_rows(h->p.ny, world, hi, &hi_y0, &hi_rows);
+  const long long lo_ps = plane_stride(lo_rows, nx, h->pad), hi_ps = plane_stride(hi_rows, nx, h->pad);
+
+  if (c->halo == HALO_NCCL) {
+    // ghost stores of the kernel land in a scratch row; the real halo moves by send/recv
+    CK(cudaMalloc(&c->dummy_ghost, sizeof(float) * (size_t)nx));
+    for (int b = 0; b < 2; b++)
+      for (int i = 0; i < 3; i++) s.ghost_lo[b][i] = s.ghost_hi[b][i] = c->dummy_ghost;
+    c->ready = true;
+    return 0;
+  }
+
+  // exchange CUDA-IPC handles of the slab allocations through the communicator
+  cudaIpcMemHandle_t mine;
+  CK(cudaIpcGetMemHandle(&mine, s.base));
+  char* d_all = nullptr;
+  const size_t hb = sizeof(cudaIpcMemHandle_t);
+  CK(cudaMalloc(&d_all, hb * (world + 1)));
+  CK(cudaMemcpy(d_all + hb * world, &mine, hb, cudaMemcpyHostToDevice));
+  NK(n->AllGather(d_all + hb * world, d_all, hb, ncclChar, c->nccl, s.stream));
+  CK(cudaStreamSynchronize(s.stream));
+  std::vector<cudaIpcMemHandle_t> all(world);
+  CK(cudaMemcpy(all.data(), d_all, hb * world, cudaMemcpyDeviceToHost));
+  CK(cudaFree(d_all));
+  CK(cudaIpcOpenMemHandle(&c->peer_lo, all[lo], cudaIpcMemLazyEnablePeerAccess));
+  if (hi == lo) c->peer_hi = c->peer_lo;
+  else CK(cudaIpcOpenMemHandle(&c->peer_hi, all[hi], cudaIpcMemLazyEnablePeerAccess));
+
+  wire_ghosts(s, nx, (char*)c->peer_lo, lo_rows, lo_ps, (char*)c->peer_hi, hi_ps);
+  // my lower neighbour counts me as its UPPER neighbour (its sync[1]); the upper one as its LOWER
+  c->peer_lo_flag = reinterpret_cast<unsigned*>(reinterpret_cast<float*>(c->peer_lo) + 18 * lo_ps) + 1;
+  c->peer_hi_flag = reinterpret_cast<unsigned*>(reinterpret_cast<float*>(c->peer_hi) + 18 * hi_ps) + 0;
+  if (comm_barrier(h)) return 1;
+  c->ready = true;
   return 0;
 }
 
@@ -485,15 +749,37 @@ int lbm_create(lbm_lattice** out, const lbm_params* params, const int* obstacles
 int lbm_create_rank(lbm_lattice** out, const lbm_params* params, const int* obstacles_slab,
                     int rank, int world, int device, const void* nccl_unique_id)
 {
-  (void)nccl_unique_id;
   if (world == 1 && rank == 0) return create_impl(out, params, obstacles_slab, device, 1);
-  return fail("lbm_create_rank: world > 1 not available in this build");
+  if (common_checks(out, params, obstacles_slab)) return 1;
+  if (world < 1 || rank < 0 || rank >= world) return fail("lbm_create_rank: rank %d of %d", rank, world);
+  if (params->ny / world < 3)
+    return fail("lbm_create_rank: %d rows cannot be split into %d slabs of >= 3 rows", params->ny, world);
+  lbm_lattice* h = new_lattice(params, world);
+  h->slabs.resize(1);
+  Slab& s = h->slabs[0];
+  s.device = device;
+  s.rank = rank;
+  lbm_slab_rows(params->ny, world, rank, &s.y0, &s.rows);
+  h->host_y0 = s.y0;
+  if (create_slab(h, s, obstacles_slab, &h->tot_cells) || attach_comm(h, rank, world, nccl_unique_id)) {
+    lbm_destroy(h);
+    return 1;
+  }
+  set_config_string(h);
+  *out = h;
+  return 0;
 }
 
 int lbm_comm_unique_id(void* out128)
 {
-  (void)out128;
-  return fail("lbm_comm_unique_id: not available in this build");
+  NcclApi* n = nccl_api();
+  if (!n) return fail("lbm_comm_unique_id: libnccl.so.2 could not be loaded");
+  if (!out128) return fail("null argument");
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes in the C ABI");
+  ncclUniqueId id;
+  NK(n->GetUniqueId(&id));
+  memcpy(out128, &id, sizeof id);
+  return 0;
 }
 
 void lbm_destroy(lbm_lattice* h)
@@ -502,8 +788,26 @@ void lbm_destroy(lbm_lattice* h)
   for (auto& s : h->slabs) {
     cudaSetDevice(s.device);
     if (s.stream) cudaStreamSynchronize(s.stream);
+  }
+  if (h->comm) {
+    Comm* c = h->comm;
+    NcclApi* n = nccl_api();
+    if (c->nccl && n && c->ready) {        // nobody unmaps memory a peer may still write to
+      Slab& s = h->slabs[0];
+      n->AllReduce(c->scratch64, c->scratch64, 1, ncclInt64, ncclSum, c->nccl, s.stream);
+      cudaStreamSynchronize(s.stream);
+    }
+    if (c->peer_hi && c->peer_hi != c->peer_lo) cudaIpcCloseMemHandle(c->peer_hi);
+    if (c->peer_lo) cudaIpcCloseMemHandle(c->peer_lo);
+    if (c->dummy_ghost) cudaFree(c->dummy_ghost);
+    if (c->scratch64) cudaFree(c->scratch64);
+    if (c->nccl && n) n->CommDestroy(c->nccl);
+    delete c;
+  }
+  for (auto& s : h->slabs) {
+    cudaSetDevice(s.device);
     drop_graphs(s);
-    for (int b = 0; b < 2; b++) if (s.buf[b]) cudaFree(s.buf[b]);
+    if (s.base) cudaFree(s.base);
     if (s.flags) cudaFree(s.flags);
     if (s.partials) cudaFree(s.partials);
     if (s.totals) cudaFree(s.totals);
@@ -529,7 +833,8 @@ int lbm_init_equilibrium(lbm_lattice* h)
     lbm::init_equilibrium_kernel<<<148 * 8, 256, 0, s.stream>>>(s.buf[h->cur], s.ps, cells, w0, w1, w2);
     CK(cudaGetLastError());
   }
-  return sync_all(h);
+  if (sync_all(h)) return 1;
+  return comm_barrier(h);
 }
 
 int lbm_upload(lbm_lattice* h, const float* const cells[9])
@@ -592,6 +897,14 @@ int lbm_av_velocity(lbm_lattice* h, float* av_vel)
     CK(cudaStreamSynchronize(s.stream));
     for (double v : part) total += v;
   }
+  if (h->comm) {
+    Slab& s = h->slabs[0];
+    double* d = reinterpret_cast<double*>(h->comm->scratch64 + 1);
+    CK(cudaMemcpy(d, &total, sizeof(double), cudaMemcpyHostToDevice));
+    NK(nccl_api()->AllReduce(d, d, 1, ncclDouble, ncclSum, h->comm->nccl, s.stream));
+    CK(cudaStreamSynchronize(s.stream));
+    CK(cudaMemcpy(&total, d, sizeof(double), cudaMemcpyDeviceToHost));
+  }
   *av_vel = (float)(total / (double)h->tot_cells);
   return 0;
 }
@@ -603,17 +916,20 @@ int lbm_macroscopic(lbm_lattice* h, float* ux, float* uy, float* speed, float* p
   for (auto& s : h->slabs) {
     CK(cudaSetDevice(s.device));
     const size_t n = (size_t)s.rows * nx;
-    float* scratch = s.buf[h->cur ^ 1];          // the idle buffer: 4 planes of it are plenty
+    float* scratch = nullptr;
+    CK(cudaMalloc(&scratch, sizeof(float) * 4 * n));
     lbm::macroscopic_kernel<<<148 * 8, 256, 0, s.stream>>>(s.buf[h->cur], s.flags, s.ps, nx, s.rows,
-                                                         h->p.density, scratch, scratch + s.ps,
-                                                         scratch + 2 * s.ps, scratch + 3 * s.ps);
+                                                         h->p.density, scratch, scratch + n,
+                                                         scratch + 2 * n, scratch + 3 * n);
     CK(cudaGetLastError());
     float* outs[4] = {ux, uy, speed, pressure};
     for (int k = 0; k < 4; k++)
-      CK(cudaMemcpyAsync(outs[k] + (size_t)(s.y0 - h->host_y0) * nx, scratch + k * s.ps, sizeof(float) * n,
+      CK(cudaMemcpyAsync(outs[k] + (size_t)(s.y0 - h->host_y0) * nx, scratch + k * n, sizeof(float) * n,
                          cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaStreamSynchronize(s.stream));
+    CK(cudaFree(scratch));
   }
-  return sync_all(h);
+  return 0;
 }
 
 double lbm_last_run_ms(const lbm_lattice* h) { return h ? h->last_ms : 0.0; }

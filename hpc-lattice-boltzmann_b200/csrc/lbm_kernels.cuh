@@ -69,38 +69,10 @@ template <> __device__ __forceinline__ unsigned ld_flags<4>(const uint8_t* p) {
   return *reinterpret_cast<const uint32_t*>(p);
 }
 
-// populations arriving from the west neighbour (speeds 1,5,8): cells x-1 .. x+VEC-2 of `row`
-template <int VEC>
-__device__ __forceinline__ void pull_from_west(const float* row, int x, int nx, bool lane_has_it,
-                                               float (&out)[VEC])
-{
-  float a[VEC];
-  ld_vec<VEC>(row + x, a);
-  float left = __shfl_up_sync(FULL_MASK, a[VEC - 1], 1);
-  if (!lane_has_it) left = row[x == 0 ? nx - 1 : x - 1];
-  out[0] = left;
-#pragma unroll
-  for (int i = 1; i < VEC; i++) out[i] = a[i - 1];
-}
-
-// populations arriving from the east neighbour (speeds 3,6,7): cells x+1 .. x+VEC of `row`
-template <int VEC>
-__device__ __forceinline__ void pull_from_east(const float* row, int x, int nx, bool lane_has_it,
-                                               float (&out)[VEC])
-{
-  float a[VEC];
-  ld_vec<VEC>(row + x, a);
-  float right = __shfl_down_sync(FULL_MASK, a[0], 1);
-  if (!lane_has_it) right = row[x + VEC == nx ? 0 : x + VEC];
-#pragma unroll
-  for (int i = 0; i < VEC - 1; i++) out[i] = a[i + 1];
-  out[VEC - 1] = right;
-}
-
-// ---- one cell: bounce-back or BGK relaxation, optional next-step acceleration --------------
-// t[] pulled populations in, post-step populations out; returns the speed (0 for obstacles).
-__device__ __forceinline__ float relax_cell(float (&t)[9], unsigned flag, float omega, float a1,
-                                            float a2, bool fuse_accel)
+// ---- one fluid cell: BGK relaxation in place (f32-strict contract) ----------------------------
+// t[] holds the pulled populations on entry and the relaxed ones on return; returns |u|^2 of the
+// pre-collision moments (kernels.cl:198 takes the speed from the same moments).
+__device__ __forceinline__ float bgk_cell(float (&t)[9], float omega)
 {
   constexpr float W0 = (float)(4.0 / 9.0);    // float roundings of the double quotients,
   constexpr float W1 = (float)(1.0 / 9.0);    // as kernels.cl:58-61 has them
@@ -114,42 +86,39 @@ __device__ __forceinline__ float relax_cell(float (&t)[9], unsigned flag, float 
                              __fadd_rn(__fadd_rn(t[3], t[6]), t[7]));
   const float my = __fsub_rn(__fadd_rn(__fadd_rn(t[2], t[5]), t[6]),
                              __fadd_rn(__fadd_rn(t[4], t[7]), t[8]));
-  const float ux = __fdiv_rn(mx, rho);
-  const float uy = __fdiv_rn(my, rho);
+  // one correctly rounded reciprocal and two products instead of the reference's two divisions:
+  // rho is O(0.1), so the reciprocal never leaves the fast path, whereas mx/rho with mx == 0
+  // (fluid at rest: most of a freshly started channel) takes the slow IEEE-division path
+  const float inv = __frcp_rn(rho);
+  const float ux = __fmul_rn(mx, inv);
+  const float uy = __fmul_rn(my, inv);
   const float usq = __fmaf_rn(uy, uy, __fmul_rn(ux, ux));
   const float b = __fmaf_rn(-1.5f, usq, 1.0f);
   const float wr0 = __fmul_rn(W0, rho), wr1 = __fmul_rn(W1, rho), wr2 = __fmul_rn(W2, rho);
   const float u5 = __fadd_rn(ux, uy), u6 = __fsub_rn(uy, ux);
 
-  float o[9];
-  o[0] = __fmaf_rn(omega, __fsub_rn(__fmul_rn(wr0, b), t[0]), t[0]);
+  t[0] = __fmaf_rn(omega, __fsub_rn(__fmul_rn(wr0, b), t[0]), t[0]);
 #define LBM_RELAX(k, u, wr)                                                          \
   {                                                                                  \
     const float p = __fmaf_rn((u), __fmaf_rn((u), 4.5f, 3.0f), b);                   \
-    o[k] = __fmaf_rn(omega, __fsub_rn(__fmul_rn((wr), p), t[k]), t[k]);              \
+    t[k] = __fmaf_rn(omega, __fsub_rn(__fmul_rn((wr), p), t[k]), t[k]);              \
   }
   LBM_RELAX(1,  ux, wr1) LBM_RELAX(2,  uy, wr1) LBM_RELAX(3, -ux, wr1) LBM_RELAX(4, -uy, wr1)
   LBM_RELAX(5,  u5, wr2) LBM_RELAX(6,  u6, wr2) LBM_RELAX(7, -u5, wr2) LBM_RELAX(8, -u6, wr2)
 #undef LBM_RELAX
-
-  // inflow acceleration of the NEXT step, applied to the just-relaxed values of row ny-2
-  // (bit-identical to running accelerate_flow as a separate pre-pass: kernels.cl:29-41)
-  if (fuse_accel && (flag & FLAG_ACCEL)) {
-    if (__fsub_rn(o[3], a1) > 0.0f && __fsub_rn(o[6], a2) > 0.0f && __fsub_rn(o[7], a2) > 0.0f) {
-      o[1] = __fadd_rn(o[1], a1); o[5] = __fadd_rn(o[5], a2); o[8] = __fadd_rn(o[8], a2);
-      o[3] = __fsub_rn(o[3], a1); o[6] = __fsub_rn(o[6], a2); o[7] = __fsub_rn(o[7], a2);
-    }
-  }
-
-  const bool obst = flag & FLAG_OBSTACLE;
-  // rebound: opposite directions of the pulled values, rest population kept.  A select, not a
-  // 0/1 multiply as in kernels.cl:179-196, so a zero-density obstacle cell cannot leak a NaN.
-  const float r1 = t[3], r2 = t[4], r3 = t[1], r4 = t[2], r5 = t[7], r6 = t[8], r7 = t[5], r8 = t[6];
-  t[0] = obst ? t[0] : o[0];
-  t[1] = obst ? r1 : o[1]; t[2] = obst ? r2 : o[2]; t[3] = obst ? r3 : o[3]; t[4] = obst ? r4 : o[4];
-  t[5] = obst ? r5 : o[5]; t[6] = obst ? r6 : o[6]; t[7] = obst ? r7 : o[7]; t[8] = obst ? r8 : o[8];
-  return obst ? 0.0f : __fsqrt_rn(usq);
+  return usq;
 }
+
+// inflow acceleration (kernels.cl:29-41) of one fluid cell of row ny-2, on registers
+__device__ __forceinline__ void accelerate_cell(float (&t)[9], float a1, float a2)
+{
+  if (__fsub_rn(t[3], a1) > 0.0f && __fsub_rn(t[6], a2) > 0.0f && __fsub_rn(t[7], a2) > 0.0f) {
+    t[1] = __fadd_rn(t[1], a1); t[5] = __fadd_rn(t[5], a2); t[8] = __fadd_rn(t[8], a2);
+    t[3] = __fsub_rn(t[3], a1); t[6] = __fsub_rn(t[6], a2); t[7] = __fsub_rn(t[7], a2);
+  }
+}
+
+__device__ __forceinline__ void swap2(float& a, float& b) { const float c = a; a = b; b = c; }
 
 // block-wide deterministic sum (fixed shuffle tree, then fixed order over warps)
 template <int TPB>
@@ -183,34 +152,80 @@ lbm_step_kernel(const __grid_constant__ StepArgs A)
   const int c = (int)(item - (unsigned)(r - 1) * (unsigned)A.nxv);
   const int x = c * VEC;
   const int lane = threadIdx.x & 31;
-  const bool west_in_warp = lane > 0 && c > 0;
-  const bool east_in_warp = lane < 31 && c < A.nxv - 1;
+  // the element just outside my vector comes from the neighbouring lane when that lane holds the
+  // adjacent cells of the same row; otherwise (warp edge, row edge, periodic wrap) I load it
+  const bool west_by_load = !(lane > 0 && c > 0);
+  const bool east_by_load = !(lane < 31 && c < A.nxv - 1);
+  const int xw = (x == 0) ? A.nx - 1 : x - 1;
+  const int xe = (x + VEC == A.nx) ? 0 : x + VEC;
 
   const long long row_mid = (long long)r * A.nx;
   const long long row_lo = row_mid - A.nx, row_hi = row_mid + A.nx;
-  const float* s = A.src;
   const long long ps = A.ps;
+  const float* s = A.src;
+  const float* p1 = s + 1 * ps + row_mid; const float* p3 = s + 3 * ps + row_mid;
+  const float* p5 = s + 5 * ps + row_lo;  const float* p6 = s + 6 * ps + row_lo;
+  const float* p7 = s + 7 * ps + row_hi;  const float* p8 = s + 8 * ps + row_hi;
 
+  // ---- phase 1: issue EVERY global load of this thread before the first use, so that a warp
+  // pays one memory round trip per step, not one per dependent group
   float f[9][VEC];
+  float v1[VEC], v3[VEC], v5[VEC], v6[VEC], v7[VEC], v8[VEC];
+  float e1 = 0.f, e3 = 0.f, e5 = 0.f, e6 = 0.f, e7 = 0.f, e8 = 0.f;
   ld_vec<VEC>(s + row_mid + x, f[0]);
+  ld_vec<VEC>(p1 + x, v1);
   ld_vec<VEC>(s + 2 * ps + row_lo + x, f[2]);
+  ld_vec<VEC>(p3 + x, v3);
   ld_vec<VEC>(s + 4 * ps + row_hi + x, f[4]);
-  pull_from_west<VEC>(s + 1 * ps + row_mid, x, A.nx, west_in_warp, f[1]);
-  pull_from_west<VEC>(s + 5 * ps + row_lo,  x, A.nx, west_in_warp, f[5]);
-  pull_from_west<VEC>(s + 8 * ps + row_hi,  x, A.nx, west_in_warp, f[8]);
-  pull_from_east<VEC>(s + 3 * ps + row_mid, x, A.nx, east_in_warp, f[3]);
-  pull_from_east<VEC>(s + 6 * ps + row_lo,  x, A.nx, east_in_warp, f[6]);
-  pull_from_east<VEC>(s + 7 * ps + row_hi,  x, A.nx, east_in_warp, f[7]);
+  ld_vec<VEC>(p5 + x, v5);
+  ld_vec<VEC>(p6 + x, v6);
+  ld_vec<VEC>(p7 + x, v7);
+  ld_vec<VEC>(p8 + x, v8);
   const unsigned flags = ld_flags<VEC>(A.flags + row_mid + x);
+  if (west_by_load) { e1 = p1[xw]; e5 = p5[xw]; e8 = p8[xw]; }
+  if (east_by_load) { e3 = p3[xe]; e6 = p6[xe]; e7 = p7[xe]; }
 
+  // ---- phase 2: assemble the x-shifted populations (speeds 1,5,8 come from x-1; 3,6,7 from x+1)
+  {
+    const float l1 = __shfl_up_sync(FULL_MASK, v1[VEC - 1], 1);
+    const float l5 = __shfl_up_sync(FULL_MASK, v5[VEC - 1], 1);
+    const float l8 = __shfl_up_sync(FULL_MASK, v8[VEC - 1], 1);
+    const float r3 = __shfl_down_sync(FULL_MASK, v3[0], 1);
+    const float r6 = __shfl_down_sync(FULL_MASK, v6[0], 1);
+    const float r7 = __shfl_down_sync(FULL_MASK, v7[0], 1);
+    f[1][0] = west_by_load ? e1 : l1;
+    f[5][0] = west_by_load ? e5 : l5;
+    f[8][0] = west_by_load ? e8 : l8;
+    f[3][VEC - 1] = east_by_load ? e3 : r3;
+    f[6][VEC - 1] = east_by_load ? e6 : r6;
+    f[7][VEC - 1] = east_by_load ? e7 : r7;
+#pragma unroll
+    for (int i = 1; i < VEC; i++) { f[1][i] = v1[i - 1]; f[5][i] = v5[i - 1]; f[8][i] = v8[i - 1]; }
+#pragma unroll
+    for (int i = 0; i < VEC - 1; i++) { f[3][i] = v3[i + 1]; f[6][i] = v6[i + 1]; f[7][i] = v7[i + 1]; }
+  }
+
+  // ---- phase 3: per cell, rebound (obstacle) or BGK relaxation (+ next step's acceleration)
   double speed_sum = 0.0;
+  const bool fuse = A.fuse_accel != 0;
 #pragma unroll
   for (int j = 0; j < VEC; j++) {
+    const unsigned fl = (flags >> (8 * j)) & 0xffu;
     float t[9];
 #pragma unroll
     for (int k = 0; k < 9; k++) t[k] = f[k][j];
-    const float sp = relax_cell(t, (flags >> (8 * j)) & 0xffu, A.omega, A.a1, A.a2, A.fuse_accel != 0);
-    speed_sum += (double)sp;
+    if (fl & FLAG_OBSTACLE) {
+      // rebound (kernels.cl:100-107): opposite directions of the pulled values, rest population
+      // kept.  A real branch instead of the reference's 0/1 multiply (:179-196): a zero-density
+      // obstacle cell cannot leak a NaN, and fluid-only warps skip it.
+      swap2(t[1], t[3]); swap2(t[2], t[4]); swap2(t[5], t[7]); swap2(t[6], t[8]);
+    } else {
+      const float usq = bgk_cell(t, A.omega);
+      if (usq > 0.0f) speed_sum += (double)__fsqrt_rn(usq);
+      // inflow acceleration of the NEXT step on the just-relaxed values of row ny-2: bit-identical
+      // to running accelerate_flow as a separate pre-pass (kernels.cl:7-42)
+      if (fuse && (fl & FLAG_ACCEL)) accelerate_cell(t, A.a1, A.a2);
+    }
 #pragma unroll
     for (int k = 0; k < 9; k++) f[k][j] = t[k];
   }
@@ -367,6 +382,42 @@ __global__ void macroscopic_kernel(const float* buf, const uint8_t* flags, long 
     u_out[i] = __fsqrt_rn(__fadd_rn(__fmul_rn(ux, ux), __fmul_rn(uy, uy)));
     p_out[i] = __fmul_rn(rho, C_SQ);
   }
+}
+
+// ---- cross-GPU step ordering (one process per GPU: peers are other processes' memory mapped
+// through CUDA IPC, so stream events cannot order them) ---------------------------------------
+// Each rank owns two counters that its ring neighbours bump after every completed step.  Before
+// step s a rank needs both counters >= s: the neighbours' stores into its ghost rows (the input of
+// step s) have landed, and the neighbours no longer read the ghost rows it is about to overwrite.
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p)
+{
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v)
+{
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// 2 threads: thread i waits for flags[i] >= want.  Bounded: after ~4 s of SM clocks it gives up
+// and raises *timed_out instead of hanging the GPU (the host reports it as an error).
+__global__ void wait_neighbours_kernel(const unsigned* flags, unsigned want, unsigned* timed_out)
+{
+  const unsigned* f = flags + threadIdx.x;
+  const long long t0 = clock64();
+  while ((int)(ld_acquire_sys(f) - want) < 0) {
+    if (clock64() - t0 > 8000000000LL) { *timed_out = 1u; break; }
+    __nanosleep(200);
+  }
+}
+
+// runs after the step kernel in stream order: every store of that step (local and peer) is
+// complete; publish "I have finished `done` steps" to both neighbours
+__global__ void signal_neighbours_kernel(unsigned* peer_lo_flag, unsigned* peer_hi_flag, unsigned done)
+{
+  __threadfence_system();
+  st_release_sys(threadIdx.x == 0 ? peer_lo_flag : peer_hi_flag, done);
 }
 
 }  // namespace lbm

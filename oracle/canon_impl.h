@@ -121,8 +121,9 @@ static inline REAL SUFFIX(collide_cell)(const REAL* t, REAL* o, REAL omega)
   for (int k = 1; k < 9; k++) rho = rho + t[k];
   const float mx = ((t[1] + t[5]) + t[8]) - ((t[3] + t[6]) + t[7]);
   const float my = ((t[2] + t[5]) + t[6]) - ((t[4] + t[7]) + t[8]);
-  const float ux = mx / rho;
-  const float uy = my / rho;
+  const float inv = 1.0f / rho;          /* correctly rounded reciprocal == __frcp_rn */
+  const float ux = mx * inv;
+  const float uy = my * inv;
   const float usq = fmaf(uy, uy, ux * ux);
   const float b = fmaf(-1.5f, usq, 1.0f);
   const float wr0 = W0 * rho, wr1 = W1 * rho, wr2 = W2 * rho;
