@@ -143,7 +143,7 @@ def time_reference_cpu(nx_full, ny_full, steps, warmup, crop=2048, budget_s=25.0
             "ms_per_step_sample": dt / k * 1e3, "steps": k}
 
 
-def run_reference_arm(a, nx, ny):
+def run_reference_arm(a, nx, ny, emit):
     rank, world, _ = dist_env()
     if rank != 0:
         return 0
@@ -158,7 +158,7 @@ def run_reference_arm(a, nx, ny):
             "e2e": {"value": cb["value"], "unit": "MLUPS", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -188,8 +188,20 @@ def main():
     a = ap.parse_args()
     nx, ny = (int(v) for v in a.workload.lower().split("x"))
     a.warmup = max(3, a.warmup)
+    # stdout carries exactly one JSON line: anything a library prints there (NCCL's version
+    # banner, the reference's device list) is sent to stderr instead
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
+
     if a.impl == "reference":
-        return run_reference_arm(a, nx, ny)
+        return run_reference_arm(a, nx, ny, emit)
 
     rank, world, local = dist_env()
     if world != a.gpus:
@@ -312,7 +324,7 @@ def main():
                       "device; 75.5 MB double-buffered working set is L2-resident on B200, so the "
                       "fraction is against the HBM roofline but served largely from L2")
         line["extra"] = {"1024x1024": ex}
-    print(json.dumps(line))
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
     return 0
