@@ -134,6 +134,7 @@ struct Comm {
   float* dummy_ghost = nullptr;  // NCCL halo: the kernel's ghost stores go nowhere useful
   long long* scratch64 = nullptr;
   bool ready = false;            // fully attached: destroy may run its closing barrier
+  bool in_kernel = false;        // ring ordering done by the step kernel's boundary blocks
 };
 
 struct Slab {
@@ -231,6 +232,19 @@ StepArgs make_args(const lbm_lattice* h, const Slab& s, int cur, int fuse, int s
     a.ghost_hi[i] = s.ghost_hi[cur ^ 1][i];
   }
   a.partials = s.partials + (long long)slot * s.nblk;
+  if (h->comm && h->comm->halo == HALO_P2P && h->comm->in_kernel) {
+    const Comm* c = h->comm;
+    const long long last_row_first_item = (long long)(s.rows - 1) * a.nxv;
+    a.ring_in = s.sync;
+    a.ring_out_lo = c->peer_lo_flag;
+    a.ring_out_hi = c->peer_hi_flag;
+    a.ring_tickets = s.sync + 4;
+    a.ring_timeout = s.sync + 2;
+    a.ring_step = c->steps_done;
+    a.nb_hi = s.nblk - (int)(last_row_first_item / h->tpb);
+    a.nb_lo = (a.nxv + h->tpb - 1) / h->tpb;
+    a.rot = a.nb_hi;
+  }
   return a;
 }
 
@@ -402,7 +416,7 @@ int run_impl(lbm_lattice* h, int iters, double* av_out)
           CK(cudaStreamWaitEvent(s.stream, lo.ev_step[(step_no - 1) & 1], 0));
           CK(cudaStreamWaitEvent(s.stream, hi.ev_step[(step_no - 1) & 1], 0));
         }
-        if (comm && comm->halo == HALO_P2P) {
+        if (comm && comm->halo == HALO_P2P && !comm->in_kernel) {
           lbm::wait_neighbours_kernel<<<1, 2, 0, s.stream>>>(s.sync, comm->steps_done, s.sync + 2);
           CK(cudaGetLastError());
           h->last_launches++;
@@ -410,12 +424,12 @@ int run_impl(lbm_lattice* h, int iters, double* av_out)
         const StepArgs a = make_args(h, s, cur, fuse, i);
         CK(launch_step(h->vec, h->tpb, a, s.nblk, s.stream));
         if (nslab > 1) CK(cudaEventRecord(s.ev_step[step_no & 1], s.stream));
-        if (comm && comm->halo == HALO_P2P) {
+        if (comm && comm->halo == HALO_P2P && !comm->in_kernel) {
           lbm::signal_neighbours_kernel<<<1, 2, 0, s.stream>>>(comm->peer_lo_flag, comm->peer_hi_flag,
                                                                comm->steps_done + 1);
           CK(cudaGetLastError());
           h->last_launches++;
-        } else if (comm) {
+        } else if (comm && comm->halo == HALO_NCCL) {
           if (nccl_halo_exchange(h, s, cur ^ 1)) return 1;
           h->last_launches++;
         }
@@ -567,7 +581,9 @@ void wire_ghosts(Slab& s, int nx, char* lo_base, int lo_rows, long long lo_ps, c
 void set_config_string(lbm_lattice* h)
 {
   char cfg[320];
-  const char* mode = h->comm ? (h->comm->halo == HALO_NCCL ? "ranks+nccl-sendrecv" : "ranks+ipc-peer-stores")
+  const char* mode = h->comm ? (h->comm->halo == HALO_NCCL ? "ranks+nccl-sendrecv"
+                                : h->comm->in_kernel ? "ranks+ipc-peer-stores+in-kernel-ring"
+                                                     : "ranks+ipc-peer-stores+wait/signal-kernels")
                              : (h->slabs.size() > 1 ? "one-process+peer-stores" : "single-gpu");
   snprintf(cfg, sizeof cfg, "vec=%d tpb=%d chunk=%d graph=%d slabs=%d halo=%s plane_stride=%lld",
            h->vec, h->tpb, h->chunk, (int)(h->use_graph && h->world == 1), h->world, mode,
@@ -714,6 +730,11 @@ int attach_comm(lbm_lattice* h, int rank, int world, const void* unique_id)
   // my lower neighbour counts me as its UPPER neighbour (its sync[1]); the upper one as its LOWER
   c->peer_lo_flag = reinterpret_cast<unsigned*>(reinterpret_cast<float*>(c->peer_lo) + 18 * lo_ps) + 1;
   c->peer_hi_flag = reinterpret_cast<unsigned*>(reinterpret_cast<float*>(c->peer_hi) + 18 * hi_ps) + 0;
+  // Ring ordering inside the step kernel needs every row to start on its own 128-byte line (an
+  // interior block must not pull a stale copy of a ghost row's tail into L1 before the boundary
+  // block has seen the neighbour's flag); otherwise two tiny wait/signal launches bracket each step.
+  const char* ring = getenv("LBM_RING");
+  c->in_kernel = (nx % 32 == 0) && !(ring && !strcmp(ring, "kernels"));
   if (comm_barrier(h)) return 1;
   c->ready = true;
   return 0;

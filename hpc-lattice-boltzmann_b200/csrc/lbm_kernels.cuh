@@ -28,6 +28,28 @@ constexpr unsigned FULL_MASK = 0xffffffffu;
 constexpr int FLAG_OBSTACLE = 1;   // cell is blocked (d2q9-bgk.c:627)
 constexpr int FLAG_ACCEL    = 2;   // fluid cell of global row ny-2 (kernels.cl:21,29)
 
+// system-scope flag accesses for the cross-GPU ring ordering
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p)
+{
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v)
+{
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// bounded spin until *flag >= want (wrap-safe); gives up after ~4 s of SM clocks and raises
+// *timed_out instead of hanging the GPU -- the host turns that into an error
+__device__ __forceinline__ void spin_until(const unsigned* flag, unsigned want, unsigned* timed_out)
+{
+  const long long t0 = clock64();
+  while ((int)(ld_acquire_sys(flag) - want) < 0) {
+    if (clock64() - t0 > 8000000000LL) { *timed_out = 1u; break; }
+    __nanosleep(100);
+  }
+}
+
 struct StepArgs {
   const float*   src;        // 9 planes, plane k at src + k*ps, storage row r at + r*nx
   float*         dst;
@@ -40,6 +62,15 @@ struct StepArgs {
   float*         ghost_lo[3];// row base receiving planes 4,7,8 of the first owned row
   float*         ghost_hi[3];// row base receiving planes 2,5,6 of the last owned row
   double*        partials;   // [gridDim.x] per-block sums of cell speeds for this step
+  // one-process-per-GPU ring ordering done by the boundary blocks themselves (null = not used):
+  const unsigned* ring_in;   // [0] steps finished by my lower neighbour's top row, [1] by my upper's bottom row
+  unsigned*      ring_out_lo;// lower neighbour's ring_in[1]
+  unsigned*      ring_out_hi;// upper neighbour's ring_in[0]
+  unsigned*      ring_tickets;// [2] boundary blocks of this step that are done (lo side, hi side)
+  unsigned*      ring_timeout;
+  unsigned       ring_step;  // number of steps every rank has completed before this one
+  int            rot;        // block-id rotation: the blocks holding the last row run first
+  int            nb_lo, nb_hi;// how many blocks touch the first / the last owned row
 };
 
 // ---- vector access helpers ---------------------------------------------------------------
@@ -145,7 +176,28 @@ template <int VEC, int TPB>
 __global__ void __launch_bounds__(TPB)
 lbm_step_kernel(const __grid_constant__ StepArgs A)
 {
-  const unsigned gid = blockIdx.x * TPB + threadIdx.x;     // nvec < 2^31 is checked at create
+  // the blocks that hold the slab's last row are rotated to the front of the grid (rot = how many),
+  // so both boundary rows are computed -- and their halos are on the wire -- first
+  const unsigned vb = A.rot == 0 ? blockIdx.x
+                      : (blockIdx.x < (unsigned)A.rot ? gridDim.x - A.rot + blockIdx.x : blockIdx.x - A.rot);
+  bool ring_lo = false, ring_hi = false;
+  if (A.ring_in != nullptr) {
+    // Only the blocks that touch a boundary row take part in the cross-GPU ordering.  Before
+    // step s they need "neighbour's adjacent boundary row has finished step s-1": its stores into
+    // my ghost row (my input) have landed and it no longer reads the ghost row I will overwrite.
+    const unsigned first = vb * TPB;
+    const unsigned last = min(first + TPB, (unsigned)A.nvec) - 1u;
+    ring_lo = first < (unsigned)A.nxv;
+    ring_hi = last >= (unsigned)(A.rows - 1) * (unsigned)A.nxv;
+    if (ring_lo || ring_hi) {
+      if (threadIdx.x == 0) {
+        if (ring_lo) spin_until(A.ring_in + 0, A.ring_step, A.ring_timeout);
+        if (ring_hi) spin_until(A.ring_in + 1, A.ring_step, A.ring_timeout);
+      }
+      __syncthreads();
+    }
+  }
+  const unsigned gid = vb * TPB + threadIdx.x;             // nvec < 2^31 is checked at create
   const bool active = gid < (unsigned)A.nvec;
   const unsigned item = active ? gid : (unsigned)A.nvec - 1u;   // idle tail threads shadow the last item
   const int r = (int)(item / (unsigned)A.nxv) + 1;         // storage row (1..rows)
@@ -248,8 +300,27 @@ lbm_step_kernel(const __grid_constant__ StepArgs A)
     speed_sum = 0.0;
   }
 
+  if (ring_lo || ring_hi) {
+    // my stores (local rows and the neighbour's ghost row over NVLink) are ordered before the
+    // ticket; the last boundary block of a side publishes "step ring_step done" to that neighbour
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      if (ring_lo && atomicAdd(A.ring_tickets + 0, 1u) == (unsigned)A.nb_lo - 1u) {
+        A.ring_tickets[0] = 0u;
+        __threadfence_system();
+        st_release_sys(A.ring_out_lo, A.ring_step + 1u);
+      }
+      if (ring_hi && atomicAdd(A.ring_tickets + 1, 1u) == (unsigned)A.nb_hi - 1u) {
+        A.ring_tickets[1] = 0u;
+        __threadfence_system();
+        st_release_sys(A.ring_out_hi, A.ring_step + 1u);
+      }
+    }
+  }
+
   const double total = block_sum<TPB>(speed_sum);
-  if (threadIdx.x == 0) A.partials[blockIdx.x] = total;
+  if (threadIdx.x == 0) A.partials[vb] = total;
 }
 
 // ---- small kernels ---------------------------------------------------------------------------
@@ -389,27 +460,11 @@ __global__ void macroscopic_kernel(const float* buf, const uint8_t* flags, long 
 // Each rank owns two counters that its ring neighbours bump after every completed step.  Before
 // step s a rank needs both counters >= s: the neighbours' stores into its ghost rows (the input of
 // step s) have landed, and the neighbours no longer read the ghost rows it is about to overwrite.
-__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p)
-{
-  unsigned v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v)
-{
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
 // 2 threads: thread i waits for flags[i] >= want.  Bounded: after ~4 s of SM clocks it gives up
 // and raises *timed_out instead of hanging the GPU (the host reports it as an error).
 __global__ void wait_neighbours_kernel(const unsigned* flags, unsigned want, unsigned* timed_out)
 {
-  const unsigned* f = flags + threadIdx.x;
-  const long long t0 = clock64();
-  while ((int)(ld_acquire_sys(f) - want) < 0) {
-    if (clock64() - t0 > 8000000000LL) { *timed_out = 1u; break; }
-    __nanosleep(200);
-  }
+  spin_until(flags + threadIdx.x, want, timed_out);
 }
 
 // runs after the step kernel in stream order: every store of that step (local and peer) is

@@ -252,18 +252,97 @@ def test_one_process_row_slabs_bit_exact(lbm, ngpus):
         assert_state_bit_exact(lat.macroscopic(), o.macroscopic(f))
 
 
-@pytest.mark.parametrize("world,halo", [(2, "p2p"), (2, "nccl"), (4, "p2p"), (8, "p2p")])
-def test_one_process_per_gpu_bit_exact(lbm, world, halo):
-    """lbm_create_rank under torch.distributed.run: IPC peer stores (default) or NCCL send/recv"""
+@pytest.mark.parametrize("world,halo,nx", [(2, "p2p", 512), (2, "p2p-kernels", 512), (2, "p2p", 516),
+                                           (2, "nccl", 512), (3, "p2p", 1024), (4, "p2p", 512),
+                                           (8, "p2p", 512), (8, "p2p-kernels", 512)])
+def test_one_process_per_gpu_bit_exact(lbm, world, halo, nx):
+    """lbm_create_rank under torch.distributed.run.  p2p: halos by peer stores into CUDA-IPC mapped
+    neighbour memory, ring ordering by the step kernel's own boundary blocks (nx % 32 == 0) or by
+    wait/signal kernels (nx = 516, or LBM_RING=kernels); nccl: ncclSend/ncclRecv halos."""
     if _gpus(lbm) < world:
         pytest.skip("needs %d GPUs" % world)
     import sys
-    env = dict(os.environ, LBM_HALO=halo)
+    env = dict(os.environ, LBM_HALO="nccl" if halo == "nccl" else "p2p")
+    if halo == "p2p-kernels":
+        env["LBM_RING"] = "kernels"
+    port = 29600 + world * 10 + ["p2p", "p2p-kernels", "nccl"].index(halo) + (3 if nx == 516 else 0)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
-           "--master-addr", "127.0.0.1", "--master-port", str(29600 + world + (7 if halo == "nccl" else 0)),
-           os.path.join(cases.ROOT, "tools", "multirank_check.py"), "--nx", "512", "--ny", "100",
+           "--master-addr", "127.0.0.1", "--master-port", str(port),
+           os.path.join(cases.ROOT, "tools", "multirank_check.py"), "--nx", str(nx), "--ny", "100",
            "--steps", "40"]
     r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=300)
     print(r.stdout[-600:])
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "-> OK" in r.stdout
+    want = {"nccl": "nccl-sendrecv", "p2p-kernels": "wait/signal-kernels",
+            "p2p": "in-kernel-ring" if nx % 32 == 0 else "wait/signal-kernels"}[halo]
+    assert want in r.stdout
+
+
+# ---- edge cases of the acceleration mask and of the geometry ------------------------------------
+@pytest.mark.parametrize("accel,blocked_row", [(1.0, False), (3.0, False), (0.01, True)])
+def test_acceleration_mask_edge_cases(lbm, accel, blocked_row):
+    """accel = 1.0 puts w1 = density*accel/9 right at the size of f3, so the `f - w > 0` test of
+    kernels.cl:29-32 is true for some cells and false for others; accel = 3.0 makes it false
+    everywhere; a fully blocked row ny-2 must leave the flow unforced"""
+    case = cases.random_case(96, 24, seed=31, accel=accel)
+    if blocked_row:
+        case.obstacles[case.ny - 2, :] = 1
+    f0 = cases.perturbed_state(case, seed=31, amp=0.2)
+    o = Oracle("f32b200", case)
+    f = f0.copy()
+    av = o.run(f, 25)
+    with make(lbm, case) as lat:
+        lat.upload(f0)
+        av_gpu = lat.run(25, f64=True)
+        assert_state_bit_exact(lat.download(), f)
+        assert np.max(np.abs(av_gpu - av) / np.abs(av)) <= 1e-12
+
+
+@pytest.mark.parametrize("nx,ny", [(4, 64), (8, 33), (1000, 37), (2, 9), (1, 6), (3, 3)])
+def test_narrow_and_ragged_grids(lbm, nx, ny):
+    case = cases.random_case(nx, ny, seed=nx * 31 + ny, fill=0.05)
+    f0 = cases.perturbed_state(case, seed=nx)
+    if case.tot_cells == 0:
+        pytest.skip("all cells blocked")
+    o = Oracle("f32b200", case)
+    f = f0.copy()
+    o.run(f, 11)
+    with make(lbm, case) as lat:
+        lat.upload(f0)
+        lat.run(11)
+        assert_state_bit_exact(lat.download(), f)
+
+
+def test_zero_iterations_and_reupload(lbm):
+    case = cases.random_case(64, 16, seed=3)
+    f0 = cases.perturbed_state(case, seed=3)
+    with make(lbm, case) as lat:
+        lat.upload(f0)
+        assert lat.run(0).size == 0
+        assert_state_bit_exact(lat.download(), f0)
+        lat.run(3)
+        lat.upload(f0)                         # a fresh upload resets the ghost rows too
+        o = Oracle("f32b200", case)
+        f = f0.copy()
+        o.run(f, 4)
+        lat.run(4)
+        assert_state_bit_exact(lat.download(), f)
+
+
+def test_executable_on_two_gpus(lbm, tmp_path):
+    """LBM_GPUS=2: same outputs as one GPU, byte for byte (state) / to reduction order (av_vels)"""
+    if _gpus(lbm) < 2:
+        pytest.skip("needs 2 GPUs")
+    case = cases.shipped("128x256")
+    outs = {}
+    for n in (1, 2):
+        d = tmp_path / ("g%d" % n)
+        d.mkdir()
+        pf, of = case.write(str(d), iters=3000)
+        r = subprocess.run([lbm.EXE_PATH, pf, of], cwd=d, capture_output=True, text=True,
+                           env=dict(os.environ, LBM_GPUS=str(n)))
+        assert r.returncode == 0, r.stderr
+        outs[n] = (open(d / "final_state.dat", "rb").read(), np.loadtxt(d / "av_vels.dat", usecols=[1]))
+    assert outs[1][0] == outs[2][0]
+    assert np.max(np.abs(outs[1][1] - outs[2][1]) / outs[1][1]) <= 1.2e-7
