@@ -186,6 +186,7 @@ struct lbm_lattice {
   int host_y0 = 0;             // first lattice row of the caller's host planes (rank mode: the slab's)
   int vec = 4, tpb = 128, chunk = 128, pad = 0;
   bool use_graph = true;
+  bool use_pdl = false;        // programmatic dependent launch between consecutive steps (1 GPU)
   double last_ms = 0;
   long long last_launches = 0;
   std::string config;
@@ -196,15 +197,28 @@ namespace {
 using lbm::StepArgs;
 
 template <int VEC, int TPB>
-cudaError_t launch_step_t(const StepArgs& a, int nblk, cudaStream_t st)
+cudaError_t launch_step_t(const StepArgs& a, int nblk, cudaStream_t st, bool pdl)
 {
-  lbm::lbm_step_kernel<VEC, TPB><<<nblk, TPB, 0, st>>>(a);
-  return cudaGetLastError();
+  if (!pdl) {
+    lbm::lbm_step_kernel<VEC, TPB><<<nblk, TPB, 0, st>>>(a);
+    return cudaGetLastError();
+  }
+  // programmatic dependent launch on the previous kernel of the stream (see the kernel prologue)
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)nblk);
+  cfg.blockDim = dim3(TPB);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, lbm::lbm_step_kernel<VEC, TPB>, a);
 }
 
-cudaError_t launch_step(int vec, int tpb, const StepArgs& a, int nblk, cudaStream_t st)
+cudaError_t launch_step(int vec, int tpb, const StepArgs& a, int nblk, cudaStream_t st, bool pdl = false)
 {
-#define LBM_CASE(V, T) if (vec == V && tpb == T) return launch_step_t<V, T>(a, nblk, st);
+#define LBM_CASE(V, T) if (vec == V && tpb == T) return launch_step_t<V, T>(a, nblk, st, pdl);
   LBM_CASE(4, 64) LBM_CASE(4, 128) LBM_CASE(4, 256) LBM_CASE(4, 512)
   LBM_CASE(2, 64) LBM_CASE(2, 128) LBM_CASE(2, 256) LBM_CASE(2, 512)
   LBM_CASE(1, 64) LBM_CASE(1, 128) LBM_CASE(1, 256) LBM_CASE(1, 512)
@@ -345,7 +359,7 @@ int build_graph(lbm_lattice* h, Slab& s, int cur)
   int c = cur;
   for (int i = 0; i < h->chunk; i++) {
     const StepArgs a = make_args(h, s, c, 1, i);
-    CK(launch_step(h->vec, h->tpb, a, s.nblk, s.stream));
+    CK(launch_step(h->vec, h->tpb, a, s.nblk, s.stream, h->use_pdl && i > 0));
     c ^= 1;
   }
   lbm::reduce_partials_kernel<<<h->chunk, 256, 0, s.stream>>>(s.partials, s.nblk, s.totals, s.counter);
@@ -422,7 +436,7 @@ int run_impl(lbm_lattice* h, int iters, double* av_out)
           h->last_launches++;
         }
         const StepArgs a = make_args(h, s, cur, fuse, i);
-        CK(launch_step(h->vec, h->tpb, a, s.nblk, s.stream));
+        CK(launch_step(h->vec, h->tpb, a, s.nblk, s.stream, h->use_pdl && nslab == 1 && !comm && i > 0));
         if (nslab > 1) CK(cudaEventRecord(s.ev_step[step_no & 1], s.stream));
         if (comm && comm->halo == HALO_P2P && !comm->in_kernel) {
           lbm::signal_neighbours_kernel<<<1, 2, 0, s.stream>>>(comm->peer_lo_flag, comm->peer_hi_flag,
@@ -509,6 +523,7 @@ void read_tuning(lbm_lattice* h)
   h->tpb = (want_tpb == 64 || want_tpb == 256 || want_tpb == 512) ? want_tpb : 128;
   h->chunk = std::max(2, env_int("LBM_CHUNK", 128)) & ~1;
   h->use_graph = env_int("LBM_GRAPH", 1) != 0;
+  h->use_pdl = env_int("LBM_PDL", -1) != 0;   // -1 = decide per slab size (create_slab)
   h->pad = std::max(0, env_int("LBM_PLANE_PAD", 0));
 }
 
@@ -521,6 +536,9 @@ int create_slab(lbm_lattice* h, Slab& s, const int* obstacles_rows, long long* f
   s.nvec = (long long)s.rows * (nx / h->vec);
   if (s.nvec >= (1LL << 31)) return fail("lbm_create: slab too large for 32-bit work index");
   s.nblk = (int)((s.nvec + h->tpb - 1) / h->tpb);
+  // PDL pays once a step is longer than a launch: measured +2 % at 1024^2 (2048 blocks), +10 % at
+  // 128^2 but -50 % at 256^2 inside graphs (profiles/r1_tuning.md), so auto = multi-wave grids only
+  if (env_int("LBM_PDL", -1) < 0) h->use_pdl = s.nblk >= 148 * 8;
   s.owns_accel_row = (ny - 2 >= s.y0 && ny - 2 < s.y0 + s.rows);
   s.accel_row = ny - 2 - s.y0 + 1;
 
@@ -585,8 +603,9 @@ void set_config_string(lbm_lattice* h)
                                 : h->comm->in_kernel ? "ranks+ipc-peer-stores+in-kernel-ring"
                                                      : "ranks+ipc-peer-stores+wait/signal-kernels")
                              : (h->slabs.size() > 1 ? "one-process+peer-stores" : "single-gpu");
-  snprintf(cfg, sizeof cfg, "vec=%d tpb=%d chunk=%d graph=%d slabs=%d halo=%s plane_stride=%lld",
-           h->vec, h->tpb, h->chunk, (int)(h->use_graph && h->world == 1), h->world, mode,
+  snprintf(cfg, sizeof cfg, "vec=%d tpb=%d chunk=%d graph=%d pdl=%d slabs=%d halo=%s plane_stride=%lld",
+           h->vec, h->tpb, h->chunk, (int)(h->use_graph && h->world == 1),
+           (int)(h->use_pdl && h->world == 1), h->world, mode,
            h->slabs[0].ps);
   h->config = cfg;
 }

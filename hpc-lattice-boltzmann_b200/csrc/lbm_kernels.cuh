@@ -176,6 +176,10 @@ template <int VEC, int TPB>
 __global__ void __launch_bounds__(TPB)
 lbm_step_kernel(const __grid_constant__ StepArgs A)
 {
+  // Programmatic dependent launch: let the NEXT step's grid be scheduled as soon as every block of
+  // this one is resident; its blocks park at griddepcontrol.wait (below) until this grid has
+  // completed and flushed, so launch latency and block ramp-up hide under the previous step's tail.
+  asm volatile("griddepcontrol.launch_dependents;");
   // the blocks that hold the slab's last row are rotated to the front of the grid (rot = how many),
   // so both boundary rows are computed -- and their halos are on the wire -- first
   const unsigned vb = A.rot == 0 ? blockIdx.x
@@ -224,6 +228,9 @@ lbm_step_kernel(const __grid_constant__ StepArgs A)
   float f[9][VEC];
   float v1[VEC], v3[VEC], v5[VEC], v6[VEC], v7[VEC], v8[VEC];
   float e1 = 0.f, e3 = 0.f, e5 = 0.f, e6 = 0.f, e7 = 0.f, e8 = 0.f;
+  const unsigned flags = ld_flags<VEC>(A.flags + row_mid + x);   // constant data: may precede the wait
+  // everything below reads what the previous step wrote (and overwrites what it read)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   ld_vec<VEC>(s + row_mid + x, f[0]);
   ld_vec<VEC>(p1 + x, v1);
   ld_vec<VEC>(s + 2 * ps + row_lo + x, f[2]);
@@ -233,7 +240,6 @@ lbm_step_kernel(const __grid_constant__ StepArgs A)
   ld_vec<VEC>(p6 + x, v6);
   ld_vec<VEC>(p7 + x, v7);
   ld_vec<VEC>(p8 + x, v8);
-  const unsigned flags = ld_flags<VEC>(A.flags + row_mid + x);
   if (west_by_load) { e1 = p1[xw]; e5 = p5[xw]; e8 = p8[xw]; }
   if (east_by_load) { e3 = p3[xe]; e6 = p6[xe]; e7 = p7[xe]; }
 
