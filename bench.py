@@ -106,10 +106,13 @@ def time_reference_cpu(nx_full, ny_full, steps, warmup, crop=2048, budget_s=25.0
     against the host-memory OpenCL shim; OpenMP over the NDRange in the shim) on a square crop of
     the workload: the reference's kernel indexing only works for nx == ny (quirk Q1) and one step
     of the full grid would take ~10 s of CPU.  Returns a dict for "cpu_baseline"."""
+    # every host thread this process may use; torch.distributed.run exports OMP_NUM_THREADS=1, and
+    # libgomp reads the variable once, when the checker library pulls it in (not loaded before here)
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    os.environ["OMP_NUM_THREADS"] = str(cores)
     from oracle_bindings import REF_LIB, Oracle, Reference
     n = min(crop, nx_full, ny_full)
     case = cases.channel(n, n)
-    cores = os.cpu_count() or 1
     tmp = tempfile.mkdtemp(prefix="lbm_ref_")
     try:
         if os.path.isfile(REF_LIB):
@@ -137,7 +140,7 @@ def time_reference_cpu(nx_full, ny_full, steps, warmup, crop=2048, budget_s=25.0
         shutil.rmtree(tmp, ignore_errors=True)
     mlups = n * n * k / dt / 1e6
     return {"value": mlups, "unit": "MLUPS", "cores": cores, "kind": kind,
-            "threads": int(os.environ.get("OMP_NUM_THREADS", cores)),
+            "threads": cores,
             "sample": "%dx%d square crop of the %dx%d channel (same generator and seed), %d timesteps "
                       "of the reference's timestep(); %.2f s" % (n, n, nx_full, ny_full, k, dt),
             "ms_per_step_sample": dt / k * 1e3, "steps": k}
@@ -180,7 +183,7 @@ def time_case_on_gpu(lbm, case_name, steps, warmup):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="16384x16384")

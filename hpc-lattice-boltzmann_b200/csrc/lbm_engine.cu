@@ -135,6 +135,13 @@ struct Comm {
   long long* scratch64 = nullptr;
   bool ready = false;            // fully attached: destroy may run its closing barrier
   bool in_kernel = false;        // ring ordering done by the step kernel's boundary blocks
+  // LBM_REDUCE=step: one 8-byte ncclAllReduce per timestep (on a side stream, so the next step
+  // does not wait for it) instead of one all-gather of the per-step totals after the run
+  bool per_step_allreduce = false;
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_side = nullptr;
+  double* step_sums = nullptr;
+  long long step_sums_cap = 0;
 };
 
 struct Slab {
@@ -414,7 +421,13 @@ int run_impl(lbm_lattice* h, int iters, double* av_out)
 
   // remaining steps as plain launches, reduced chunk by chunk; the very last step of the run
   // leaves the state un-accelerated
-  long long step_no = 0;
+  long long step_no = 0;     // steps launched one by one in this run (graph chunks never coexist with them)
+  if (comm && comm->per_step_allreduce && comm->step_sums_cap < iters) {
+    if (comm->step_sums) CK(cudaFree(comm->step_sums));
+    comm->step_sums = nullptr;
+    CK(cudaMalloc(&comm->step_sums, sizeof(double) * h->slabs[0].totals_cap));
+    comm->step_sums_cap = h->slabs[0].totals_cap;
+  }
   while (remaining > 0) {
     const int n = std::min(remaining, h->chunk);
     for (int i = 0; i < n; i++, step_no++) {
@@ -448,22 +461,41 @@ int run_impl(lbm_lattice* h, int iters, double* av_out)
           h->last_launches++;
         }
       }
+      if (comm && comm->per_step_allreduce) {
+        // the north-star formulation: this step's slab total -> all ranks, right away
+        Slab& s = h->slabs[0];
+        const long long idx = step_no;
+        lbm::reduce_partials_kernel<<<1, 256, 0, s.stream>>>(s.partials + (long long)i * s.nblk, s.nblk,
+                                                            s.totals + idx, comm->scratch64);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(comm->ev_side, s.stream));
+        CK(cudaStreamWaitEvent(comm->side, comm->ev_side, 0));
+        NK(nccl_api()->AllReduce(s.totals + idx, comm->step_sums + idx, 1, ncclDouble, ncclSum,
+                                 comm->nccl, comm->side));
+        h->last_launches += 2;
+      }
       if (comm) comm->steps_done++;
       h->last_launches += (long long)nslab;
       cur ^= 1;
     }
-    for (auto& s : h->slabs) {
-      CK(cudaSetDevice(s.device));
-      lbm::reduce_partials_kernel<<<n, 256, 0, s.stream>>>(s.partials, s.nblk, s.totals, s.counter);
-      CK(cudaGetLastError());
-      lbm::advance_counter_kernel<<<1, 1, 0, s.stream>>>(s.counter, n);
-      CK(cudaGetLastError());
+    if (!(comm && comm->per_step_allreduce)) {
+      for (auto& s : h->slabs) {
+        CK(cudaSetDevice(s.device));
+        lbm::reduce_partials_kernel<<<n, 256, 0, s.stream>>>(s.partials, s.nblk, s.totals, s.counter);
+        CK(cudaGetLastError());
+        lbm::advance_counter_kernel<<<1, 1, 0, s.stream>>>(s.counter, n);
+        CK(cudaGetLastError());
+      }
+      h->last_launches += 2 * (long long)nslab;
     }
-    h->last_launches += 2 * (long long)nslab;
     remaining -= n;
   }
   h->cur = cur;
 
+  if (comm && comm->per_step_allreduce) {      // the run is over when its last allreduce is
+    CK(cudaEventRecord(comm->ev_side, comm->side));
+    CK(cudaStreamWaitEvent(h->slabs[0].stream, comm->ev_side, 0));
+  }
   for (auto& s : h->slabs) {
     CK(cudaSetDevice(s.device));
     CK(cudaEventRecord(s.ev_end, s.stream));
@@ -492,6 +524,11 @@ int run_impl(lbm_lattice* h, int iters, double* av_out)
       CK(cudaMemcpy(tmp.data(), s.totals, sizeof(double) * iters, cudaMemcpyDeviceToHost));
       for (int t = 0; t < iters; t++) av_out[t] += tmp[t];
     }
+  } else if (comm->per_step_allreduce) {
+    Slab& s = h->slabs[0];
+    CK(cudaStreamSynchronize(comm->side));
+    CK(cudaMemcpy(av_out, comm->step_sums, sizeof(double) * iters, cudaMemcpyDeviceToHost));
+    (void)s;
   } else {
     // all-gather every rank's per-step totals, then add them in rank order on the host
     Slab& s = h->slabs[0];
@@ -599,13 +636,14 @@ void wire_ghosts(Slab& s, int nx, char* lo_base, int lo_rows, long long lo_ps, c
 void set_config_string(lbm_lattice* h)
 {
   char cfg[320];
+  const char* red = (h->comm && h->comm->per_step_allreduce) ? " reduce=allreduce-per-step" : "";
   const char* mode = h->comm ? (h->comm->halo == HALO_NCCL ? "ranks+nccl-sendrecv"
                                 : h->comm->in_kernel ? "ranks+ipc-peer-stores+in-kernel-ring"
                                                      : "ranks+ipc-peer-stores+wait/signal-kernels")
                              : (h->slabs.size() > 1 ? "one-process+peer-stores" : "single-gpu");
-  snprintf(cfg, sizeof cfg, "vec=%d tpb=%d chunk=%d graph=%d pdl=%d slabs=%d halo=%s plane_stride=%lld",
+  snprintf(cfg, sizeof cfg, "vec=%d tpb=%d chunk=%d graph=%d pdl=%d slabs=%d halo=%s%s plane_stride=%lld",
            h->vec, h->tpb, h->chunk, (int)(h->use_graph && h->world == 1),
-           (int)(h->use_pdl && h->world == 1), h->world, mode,
+           (int)(h->use_pdl && h->world == 1), h->world, mode, red,
            h->slabs[0].ps);
   h->config = cfg;
 }
@@ -700,6 +738,10 @@ int attach_comm(lbm_lattice* h, int rank, int world, const void* unique_id)
   c->world = world;
   const char* halo = getenv("LBM_HALO");
   c->halo = (halo && !strcmp(halo, "nccl")) ? HALO_NCCL : HALO_P2P;
+  const char* red = getenv("LBM_REDUCE");
+  c->per_step_allreduce = red && !strcmp(red, "step");
+  CK(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&c->ev_side, cudaEventDisableTiming));
   ncclUniqueId id;
   memcpy(&id, unique_id, sizeof id);
   NK(n->CommInitRank(&c->nccl, world, id, rank));
@@ -840,6 +882,9 @@ void lbm_destroy(lbm_lattice* h)
     if (c->peer_hi && c->peer_hi != c->peer_lo) cudaIpcCloseMemHandle(c->peer_hi);
     if (c->peer_lo) cudaIpcCloseMemHandle(c->peer_lo);
     if (c->dummy_ghost) cudaFree(c->dummy_ghost);
+    if (c->step_sums) cudaFree(c->step_sums);
+    if (c->ev_side) cudaEventDestroy(c->ev_side);
+    if (c->side) cudaStreamDestroy(c->side);
     if (c->scratch64) cudaFree(c->scratch64);
     if (c->nccl && n) n->CommDestroy(c->nccl);
     delete c;

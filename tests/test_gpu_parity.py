@@ -253,7 +253,8 @@ def test_one_process_row_slabs_bit_exact(lbm, ngpus):
 
 
 @pytest.mark.parametrize("world,halo,nx", [(2, "p2p", 512), (2, "p2p-kernels", 512), (2, "p2p", 516),
-                                           (2, "nccl", 512), (3, "p2p", 1024), (4, "p2p", 512),
+                                           (2, "nccl", 512), (2, "p2p-allreduce", 512),
+                                           (3, "p2p", 1024), (4, "p2p", 512),
                                            (8, "p2p", 512), (8, "p2p-kernels", 512)])
 def test_one_process_per_gpu_bit_exact(lbm, world, halo, nx):
     """lbm_create_rank under torch.distributed.run.  p2p: halos by peer stores into CUDA-IPC mapped
@@ -265,7 +266,9 @@ def test_one_process_per_gpu_bit_exact(lbm, world, halo, nx):
     env = dict(os.environ, LBM_HALO="nccl" if halo == "nccl" else "p2p")
     if halo == "p2p-kernels":
         env["LBM_RING"] = "kernels"
-    port = 29600 + world * 10 + ["p2p", "p2p-kernels", "nccl"].index(halo) + (3 if nx == 516 else 0)
+    if halo == "p2p-allreduce":
+        env["LBM_REDUCE"] = "step"      # one 8-byte ncclAllReduce per timestep (north-star wording)
+    port = 29600 + world * 10 + ["p2p", "p2p-kernels", "nccl", "p2p-allreduce"].index(halo) + (4 if nx == 516 else 0)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
            "--master-addr", "127.0.0.1", "--master-port", str(port),
            os.path.join(cases.ROOT, "tools", "multirank_check.py"), "--nx", str(nx), "--ny", "100",
@@ -275,6 +278,7 @@ def test_one_process_per_gpu_bit_exact(lbm, world, halo, nx):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "-> OK" in r.stdout
     want = {"nccl": "nccl-sendrecv", "p2p-kernels": "wait/signal-kernels",
+            "p2p-allreduce": "reduce=allreduce-per-step",
             "p2p": "in-kernel-ring" if nx % 32 == 0 else "wait/signal-kernels"}[halo]
     assert want in r.stdout
 
