@@ -244,6 +244,13 @@ StepArgs make_args(const lbm_lattice* h, const Slab& s, int cur, int fuse, int s
   a.nx = h->p.nx;
   a.rows = s.rows;
   a.nxv = h->p.nx / h->vec;
+  if (a.nxv > 1) {            // magic-number division by nxv, exact for dividends < 2^31
+    int l = 0;
+    while ((1u << l) < (unsigned)a.nxv) l++;
+    const unsigned long long pw = 1ull << (31 + l);
+    a.div_mul = (unsigned)((pw + (unsigned)a.nxv - 1) / (unsigned)a.nxv);
+    a.div_shift = l - 1;
+  }
   a.omega = h->p.omega;
   a.a1 = h->a1;
   a.a2 = h->a2;

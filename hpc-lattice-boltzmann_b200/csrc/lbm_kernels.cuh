@@ -57,6 +57,8 @@ struct StepArgs {
   long long      ps;         // plane stride (floats)
   long long      nvec;       // rows * nxv work items
   int            nx, rows, nxv;
+  unsigned       div_mul;    // item / nxv == umulhi(item, div_mul) >> div_shift for item < 2^31
+  int            div_shift;  // (nxv == 1: div_mul == 0 means the quotient is the item itself)
   float          omega, a1, a2;
   int            fuse_accel; // apply the NEXT step's accelerate_flow to the values being stored
   float*         ghost_lo[3];// row base receiving planes 4,7,8 of the first owned row
@@ -173,7 +175,7 @@ __device__ __forceinline__ double block_sum(double v)
 // ---- the fused timestep --------------------------------------------------------------------
 // One thread = VEC consecutive cells of one row.  Grid = ceil(rows*nx/VEC / TPB) blocks.
 template <int VEC, int TPB>
-__global__ void __launch_bounds__(TPB)
+__global__ void __launch_bounds__(TPB, 1024 / TPB)   // 64 registers: 1024 resident threads per SM
 lbm_step_kernel(const __grid_constant__ StepArgs A)
 {
   // Programmatic dependent launch: let the NEXT step's grid be scheduled as soon as every block of
@@ -204,8 +206,9 @@ lbm_step_kernel(const __grid_constant__ StepArgs A)
   const unsigned gid = vb * TPB + threadIdx.x;             // nvec < 2^31 is checked at create
   const bool active = gid < (unsigned)A.nvec;
   const unsigned item = active ? gid : (unsigned)A.nvec - 1u;   // idle tail threads shadow the last item
-  const int r = (int)(item / (unsigned)A.nxv) + 1;         // storage row (1..rows)
-  const int c = (int)(item - (unsigned)(r - 1) * (unsigned)A.nxv);
+  const unsigned q = A.div_mul ? (__umulhi(item, A.div_mul) >> A.div_shift) : item;
+  const int r = (int)q + 1;                                // storage row (1..rows)
+  const int c = (int)(item - q * (unsigned)A.nxv);
   const int x = c * VEC;
   const int lane = threadIdx.x & 31;
   // the element just outside my vector comes from the neighbouring lane when that lane holds the
@@ -265,27 +268,31 @@ lbm_step_kernel(const __grid_constant__ StepArgs A)
 
   // ---- phase 3: per cell, rebound (obstacle) or BGK relaxation (+ next step's acceleration)
   double speed_sum = 0.0;
-  const bool fuse = A.fuse_accel != 0;
+  {
+    // (a thread-level "all my cells are plain fluid" fast path was measured 5-25 % SLOWER on B200,
+    // profiles/r1_tuning.md, so there is one generic loop)
+    const bool fuse = A.fuse_accel != 0;
 #pragma unroll
-  for (int j = 0; j < VEC; j++) {
-    const unsigned fl = (flags >> (8 * j)) & 0xffu;
-    float t[9];
+    for (int j = 0; j < VEC; j++) {
+      const unsigned fl = (flags >> (8 * j)) & 0xffu;
+      float t[9];
 #pragma unroll
-    for (int k = 0; k < 9; k++) t[k] = f[k][j];
-    if (fl & FLAG_OBSTACLE) {
-      // rebound (kernels.cl:100-107): opposite directions of the pulled values, rest population
-      // kept.  A real branch instead of the reference's 0/1 multiply (:179-196): a zero-density
-      // obstacle cell cannot leak a NaN, and fluid-only warps skip it.
-      swap2(t[1], t[3]); swap2(t[2], t[4]); swap2(t[5], t[7]); swap2(t[6], t[8]);
-    } else {
-      const float usq = bgk_cell(t, A.omega);
-      if (usq > 0.0f) speed_sum += (double)__fsqrt_rn(usq);
-      // inflow acceleration of the NEXT step on the just-relaxed values of row ny-2: bit-identical
-      // to running accelerate_flow as a separate pre-pass (kernels.cl:7-42)
-      if (fuse && (fl & FLAG_ACCEL)) accelerate_cell(t, A.a1, A.a2);
+      for (int k = 0; k < 9; k++) t[k] = f[k][j];
+      if (fl & FLAG_OBSTACLE) {
+        // rebound (kernels.cl:100-107): opposite directions of the pulled values, rest population
+        // kept.  A real branch instead of the reference's 0/1 multiply (:179-196): a zero-density
+        // obstacle cell cannot leak a NaN.
+        swap2(t[1], t[3]); swap2(t[2], t[4]); swap2(t[5], t[7]); swap2(t[6], t[8]);
+      } else {
+        const float usq = bgk_cell(t, A.omega);
+        if (usq > 0.0f) speed_sum += (double)__fsqrt_rn(usq);
+        // inflow acceleration of the NEXT step on the just-relaxed values of row ny-2:
+        // bit-identical to running accelerate_flow as a separate pre-pass (kernels.cl:7-42)
+        if (fuse && (fl & FLAG_ACCEL)) accelerate_cell(t, A.a1, A.a2);
+      }
+#pragma unroll
+      for (int k = 0; k < 9; k++) f[k][j] = t[k];
     }
-#pragma unroll
-    for (int k = 0; k < 9; k++) f[k][j] = t[k];
   }
 
   if (active) {
