@@ -58,6 +58,7 @@ def load():
         "lbm_run_f64": (C.c_int, [vp, C.c_int, dp]),
         "lbm_av_velocity": (C.c_int, [vp, fp]),
         "lbm_macroscopic": (C.c_int, [vp, fp, fp, fp, fp]),
+        "lbm_total_density": (C.c_int, [vp, dp]),
         "lbm_last_run_ms": (C.c_double, [vp]),
         "lbm_last_run_launches": (C.c_longlong, [vp]),
         "lbm_tot_cells": (C.c_longlong, [vp]),
@@ -184,6 +185,11 @@ class Lattice:
         v = C.c_float()
         _check(self.lib.lbm_av_velocity(self.h, C.byref(v)), "lbm_av_velocity")
         return np.float32(v.value)
+
+    def total_density(self):
+        v = C.c_double()
+        _check(self.lib.lbm_total_density(self.h, C.byref(v)), "lbm_total_density")
+        return v.value
 
     def macroscopic(self):
         out = np.empty((4, self.cells), dtype=np.float32)

@@ -541,13 +541,16 @@ int run_impl(lbm_lattice* h, int iters, double* av_out)
     Slab& s = h->slabs[0];
     double* gathered = nullptr;
     CK(cudaMalloc(&gathered, sizeof(double) * (size_t)iters * comm->world));
-    NK(nccl_api()->AllGather(s.totals, gathered, (size_t)iters, ncclDouble, comm->nccl, s.stream));
-    CK(cudaStreamSynchronize(s.stream));
-    for (int r = 0; r < comm->world; r++) {
-      CK(cudaMemcpy(tmp.data(), gathered + (size_t)r * iters, sizeof(double) * iters, cudaMemcpyDeviceToHost));
+    const ncclResult_t nr = nccl_api()->AllGather(s.totals, gathered, (size_t)iters, ncclDouble,
+                                                  comm->nccl, s.stream);
+    cudaError_t ce = nr == ncclSuccess ? cudaStreamSynchronize(s.stream) : cudaErrorUnknown;
+    for (int r = 0; r < comm->world && ce == cudaSuccess; r++) {
+      ce = cudaMemcpy(tmp.data(), gathered + (size_t)r * iters, sizeof(double) * iters, cudaMemcpyDeviceToHost);
       for (int t = 0; t < iters; t++) av_out[t] += tmp[t];
     }
-    CK(cudaFree(gathered));
+    cudaFree(gathered);
+    if (nr != ncclSuccess) return fail("NCCL error gathering av_vels: %s", nccl_api()->GetErrorString(nr));
+    if (ce != cudaSuccess) return fail("CUDA error gathering av_vels: %s", cudaGetErrorString(ce));
   }
   const double denom = (double)h->tot_cells;
   for (int t = 0; t < iters; t++) av_out[t] /= denom;
@@ -998,6 +1001,32 @@ int lbm_av_velocity(lbm_lattice* h, float* av_vel)
     CK(cudaMemcpy(&total, d, sizeof(double), cudaMemcpyDeviceToHost));
   }
   *av_vel = (float)(total / (double)h->tot_cells);
+  return 0;
+}
+
+int lbm_total_density(lbm_lattice* h, double* total_out)
+{
+  if (!h || !total_out) return fail("null argument");
+  double total = 0;
+  for (auto& s : h->slabs) {
+    CK(cudaSetDevice(s.device));
+    const int nblk = std::min(s.nblk, 148 * 8);
+    lbm::total_density_kernel<256><<<nblk, 256, 0, s.stream>>>(s.buf[h->cur], s.ps, h->p.nx, s.rows, s.partials);
+    CK(cudaGetLastError());
+    std::vector<double> part((size_t)nblk);
+    CK(cudaMemcpyAsync(part.data(), s.partials, sizeof(double) * nblk, cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaStreamSynchronize(s.stream));
+    for (double v : part) total += v;
+  }
+  if (h->comm) {
+    Slab& s = h->slabs[0];
+    double* d = reinterpret_cast<double*>(h->comm->scratch64 + 1);
+    CK(cudaMemcpy(d, &total, sizeof(double), cudaMemcpyHostToDevice));
+    NK(nccl_api()->AllReduce(d, d, 1, ncclDouble, ncclSum, h->comm->nccl, s.stream));
+    CK(cudaStreamSynchronize(s.stream));
+    CK(cudaMemcpy(&total, d, sizeof(double), cudaMemcpyDeviceToHost));
+  }
+  *total_out = total;
   return 0;
 }
 

@@ -436,6 +436,24 @@ av_velocity_kernel(const float* buf, const uint8_t* flags, long long ps, int nx,
   if (threadIdx.x == 0) partials[blockIdx.x] = total;
 }
 
+// total mass of a resident state (d2q9-bgk.c:822-838, the reference's DEBUG conservation check):
+// per-block double sums over every population of every cell, obstacles included
+template <int TPB>
+__global__ void __launch_bounds__(TPB)
+total_density_kernel(const float* buf, long long ps, int nx, int rows, double* partials)
+{
+  const long long n = (long long)rows * nx;
+  const long long stride = (long long)gridDim.x * TPB;
+  double acc = 0.0;
+  for (long long i = (long long)blockIdx.x * TPB + threadIdx.x; i < n; i += stride) {
+    const long long q = i + nx;
+#pragma unroll
+    for (int k = 0; k < 9; k++) acc += (double)buf[k * ps + q];
+  }
+  const double total = block_sum<TPB>(acc);
+  if (threadIdx.x == 0) partials[blockIdx.x] = total;
+}
+
 // final-state fields of write_values (d2q9-bgk.c:857-897), same float expressions
 __global__ void macroscopic_kernel(const float* buf, const uint8_t* flags, long long ps, int nx,
                                    int rows, float density, float* ux_out, float* uy_out,

@@ -85,6 +85,11 @@ int lbm_run_f64(lbm_lattice* h, int iters, double* av_vels);   /* same, un-narro
 /* `float av_velocity(params, cells, obstacles, ocl)` (d2q9-bgk.c:426-475) on the resident state */
 int lbm_av_velocity(lbm_lattice* h, float* av_vel);
 
+/* `float total_density(params, cells)` (d2q9-bgk.c:822-838): sum of every population of every cell of
+ * the resident state, accumulated in double on the device (the reference's DEBUG conservation check,
+ * which reads stale host data there; here it looks at the live state) */
+int lbm_total_density(lbm_lattice* h, double* total);
+
 /* final-state fields of write_values (d2q9-bgk.c:857-897) computed on the device: u_x, u_y, |u|,
  * pressure, nx*ny floats each (slab rows in rank mode); obstacle cells get 0,0,0,density/3 */
 int lbm_macroscopic(lbm_lattice* h, float* ux, float* uy, float* speed, float* pressure);

@@ -146,9 +146,11 @@ def test_mass_is_conserved_and_obstacle_nan_hazard(lbm):
         lat.upload(f0)
         av = lat.run(500)
         f = lat.download()
+        mass_gpu = lat.total_density()
     assert np.all(np.isfinite(av)) and np.all(np.isfinite(f))
     m0, m1 = f0.astype(np.float64).sum(), f.astype(np.float64).sum()
     assert abs(m1 - m0) / m0 < 1e-5
+    assert abs(mass_gpu - m1) <= 1e-12 * m1          # total_density (d2q9-bgk.c:822-838) on the device
 
 
 @pytest.mark.parametrize("name", cases.SHIPPED)
