@@ -152,6 +152,13 @@ struct Slab {
   char*      base = nullptr;  // one allocation: buffer 0 | buffer 1 | sync words
   float*     buf[2] = {nullptr, nullptr};
   unsigned*  sync = nullptr;  // [0] steps done by my lower neighbour, [1] by my upper, [2] timeout
+  float*     strip_lo = nullptr;   // two-step passes: t+1 rows [lower neighbour's last | my 1 | my 2]
+  float*     strip_hi = nullptr;   //                           [my rows-1 | my rows | upper neighbour's first]
+  long long  pse = 0;              // strip plane stride (floats)
+  float*     nb_lo[3] = {};        // lower neighbour's strip_hi row 2, planes 4,7,8
+  float*     nb_hi[3] = {};        // upper neighbour's strip_lo row 0, planes 2,5,6
+  int        np = 0;               // partial-sum slots per step
+  int        tiles_x = 0, tiles_y = 0;
   uint8_t*   flags = nullptr;
   double*    partials = nullptr;   // [chunk][nblk]
   double*    totals = nullptr;     // [totals_cap] per-step speed totals of this slab
@@ -178,7 +185,15 @@ long long plane_stride(int rows, int nx, int pad)
   return ((cells + 31) / 32) * 32 + ((long long)pad / 32) * 32;
 }
 
-size_t slab_bytes(long long ps) { return sizeof(float) * 18 * (size_t)ps + 256; }
+long long strip_stride(int nx) { return ((3LL * nx + 31) / 32) * 32; }
+
+// buffer 0 | buffer 1 | 256 B of sync words | strip_lo | strip_hi
+size_t slab_bytes(long long ps, int nx) { return sizeof(float) * (18 * (size_t)ps + 64 + 18 * (size_t)strip_stride(nx)); }
+
+float* strip_of(char* base, long long ps, int nx, int hi)
+{
+  return reinterpret_cast<float*>(base) + 18 * ps + 64 + (hi ? 9 * strip_stride(nx) : 0);
+}
 
 }  // namespace
 
@@ -194,6 +209,7 @@ struct lbm_lattice {
   int vec = 4, tpb = 128, chunk = 128, pad = 0;
   bool use_graph = true;
   bool use_pdl = false;        // programmatic dependent launch between consecutive steps (1 GPU)
+  bool fuse2 = false;          // two timesteps per pass through shared-memory tiles (LBM_FUSE=2)
   double last_ms = 0;
   long long last_launches = 0;
   std::string config;
@@ -259,7 +275,10 @@ StepArgs make_args(const lbm_lattice* h, const Slab& s, int cur, int fuse, int s
     a.ghost_lo[i] = s.ghost_lo[cur ^ 1][i];
     a.ghost_hi[i] = s.ghost_hi[cur ^ 1][i];
   }
-  a.partials = s.partials + (long long)slot * s.nblk;
+  a.partials = s.partials + (long long)slot * s.np;
+  a.ps_dst = s.ps;
+  a.dst_delta = 0;
+  a.push = 3;
   if (h->comm && h->comm->halo == HALO_P2P && h->comm->in_kernel) {
     const Comm* c = h->comm;
     const long long last_row_first_item = (long long)(s.rows - 1) * a.nxv;
@@ -376,7 +395,7 @@ int build_graph(lbm_lattice* h, Slab& s, int cur)
     CK(launch_step(h->vec, h->tpb, a, s.nblk, s.stream, h->use_pdl && i > 0));
     c ^= 1;
   }
-  lbm::reduce_partials_kernel<<<h->chunk, 256, 0, s.stream>>>(s.partials, s.nblk, s.totals, s.counter);
+  lbm::reduce_partials_kernel<<<h->chunk, 256, 0, s.stream>>>(s.partials, s.np, s.nblk, s.nblk, s.totals, s.counter);
   CK(cudaGetLastError());
   lbm::advance_counter_kernel<<<1, 1, 0, s.stream>>>(s.counter, h->chunk);
   CK(cudaGetLastError());
@@ -390,6 +409,89 @@ void drop_graphs(Slab& s)
 {
   for (int i = 0; i < 2; i++)
     if (s.graph[i]) { cudaGraphExecDestroy(s.graph[i]); s.graph[i] = nullptr; }
+}
+
+// ---- two-step passes (LBM_FUSE=2) ---------------------------------------------------------------
+bool fused_ok(const lbm_lattice* h)
+{
+  if (!h->fuse2 || h->slabs.size() != 1 || h->vec != 4 || h->p.nx < 128 || h->slabs[0].rows < 4) return false;
+  if (h->comm && (h->comm->halo != HALO_P2P || h->comm->per_step_allreduce)) return false;
+  return true;
+}
+
+// t -> t+2 on rows 2..rows-1 of buffer cur^1, t+1 boundary rows into the strips (slots: 2 steps)
+// tile shapes of the two-step kernel: {threads, rows relaxed to t+1, min blocks per SM}
+struct FusedCfg { int tpb, ra, minb; };
+// {256,16,2} measured best on B200 (profiles/r1_tuning.md section 7): 116 registers, 2 blocks per SM
+const FusedCfg FUSED_CFGS[] = {{256, 16, 2}, {256, 16, 3}, {256, 24, 2}, {384, 24, 2}};
+int g_fused_cfg = 0;
+
+template <int TPB, int RA, int MINB>
+int launch_fused_t(const lbm::FusedArgs& a, int ntiles, cudaStream_t st)
+{
+  static bool configured = false;
+  if (!configured) {
+    CK(cudaFuncSetAttribute(lbm::lbm_fused2_kernel<TPB, RA, MINB>,
+                            cudaFuncAttributeMaxDynamicSharedMemorySize, lbm::fused_smem(RA)));
+    configured = true;
+  }
+  lbm::lbm_fused2_kernel<TPB, RA, MINB><<<ntiles, TPB, lbm::fused_smem(RA), st>>>(a);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int launch_fused(lbm_lattice* h, Slab& s, int cur, int fuse_b, int slot)
+{
+  lbm::FusedArgs a{};
+  a.src = s.buf[cur];
+  a.dst = s.buf[cur ^ 1];
+  a.flags = s.flags;
+  a.ps = s.ps;
+  a.nx = h->p.nx;
+  a.rows = s.rows;
+  a.tiles_x = s.tiles_x;
+  a.tiles_y = s.tiles_y;
+  a.omega = h->p.omega;
+  a.a1 = h->a1;
+  a.a2 = h->a2;
+  a.fuse_b = fuse_b;
+  a.strip_lo = s.strip_lo;
+  a.strip_hi = s.strip_hi;
+  a.pse = s.pse;
+  for (int i = 0; i < 3; i++) { a.nb_lo[i] = s.nb_lo[i]; a.nb_hi[i] = s.nb_hi[i]; }
+  a.partials_a = s.partials + (long long)slot * s.np;
+  a.partials_b = s.partials + (long long)(slot + 1) * s.np;
+  const int nt = s.tiles_x * s.tiles_y;
+  switch (g_fused_cfg) {
+    case 1: return launch_fused_t<256, 16, 3>(a, nt, s.stream);
+    case 2: return launch_fused_t<256, 24, 2>(a, nt, s.stream);
+    case 3: return launch_fused_t<384, 24, 2>(a, nt, s.stream);
+    default: return launch_fused_t<256, 16, 2>(a, nt, s.stream);
+  }
+}
+
+// rows 1 and `rows` of time t+2 from the strips (which now hold the neighbours' t+1 rows too):
+// two launches of the ordinary step kernel on 3-row mini slabs; they also push the t+2 ghost rows
+int launch_fixups(lbm_lattice* h, Slab& s, int cur, int fuse_b, int slot)
+{
+  const int nx = h->p.nx, nxv = nx / h->vec;
+  const int nb_strip = (nxv + h->tpb - 1) / h->tpb;
+  const int ntiles = s.tiles_x * s.tiles_y;
+  for (int hi = 0; hi < 2; hi++) {
+    StepArgs a = make_args(h, s, cur, fuse_b, slot);
+    a.src = hi ? s.strip_hi : s.strip_lo;
+    a.ps = s.pse;
+    a.ps_dst = s.ps;
+    a.rows = 1;
+    a.nvec = nxv;
+    a.dst_delta = hi ? (long long)(s.rows - 1) * nx : 0;
+    a.push = hi ? 2 : 1;
+    a.partials = s.partials + (long long)slot * s.np + ntiles + hi * nb_strip;
+    a.ring_in = nullptr;      // ordering of two-step passes is done by the wait/signal launches
+    a.rot = 0;
+    CK(launch_step(h->vec, h->tpb, a, nb_strip, s.stream));
+  }
+  return 0;
 }
 
 int run_impl(lbm_lattice* h, int iters, double* av_out)
@@ -416,6 +518,48 @@ int run_impl(lbm_lattice* h, int iters, double* av_out)
 
   int remaining = iters;
   int cur = h->cur;
+  // ---- two timesteps per pass while at least two remain (LBM_FUSE=2)
+  if (fused_ok(h)) {
+    Slab& s = h->slabs[0];
+    const int ntiles = s.tiles_x * s.tiles_y;
+    const int nb_strip = ((h->p.nx / h->vec) + h->tpb - 1) / h->tpb;
+    while (remaining >= 2) {
+      const int pairs = std::min(remaining / 2, h->chunk / 2);
+      for (int j = 0; j < pairs; j++) {
+        const int fuse_b = (remaining - 2 * j - 2) > 0;
+        if (comm) {
+          lbm::wait_neighbours_kernel<<<1, 2, 0, s.stream>>>(s.sync, comm->steps_done, s.sync + 2);
+          CK(cudaGetLastError());
+        }
+        if (launch_fused(h, s, cur, fuse_b, 2 * j)) return 1;
+        if (comm) {   // my t+1 boundary rows are in the neighbours' strips; wait for theirs
+          lbm::signal_neighbours_kernel<<<1, 2, 0, s.stream>>>(comm->peer_lo_flag, comm->peer_hi_flag,
+                                                               comm->steps_done + 1);
+          CK(cudaGetLastError());
+          comm->steps_done++;
+          lbm::wait_neighbours_kernel<<<1, 2, 0, s.stream>>>(s.sync, comm->steps_done, s.sync + 2);
+          CK(cudaGetLastError());
+        }
+        if (launch_fixups(h, s, cur, fuse_b, 2 * j + 1)) return 1;
+        if (comm) {
+          lbm::signal_neighbours_kernel<<<1, 2, 0, s.stream>>>(comm->peer_lo_flag, comm->peer_hi_flag,
+                                                               comm->steps_done + 1);
+          CK(cudaGetLastError());
+          comm->steps_done++;
+        }
+        h->last_launches += comm ? 7 : 3;
+        cur ^= 1;
+      }
+      lbm::reduce_partials_kernel<<<2 * pairs, 256, 0, s.stream>>>(s.partials, s.np, ntiles,
+                                                                   ntiles + 2 * nb_strip, s.totals, s.counter);
+      CK(cudaGetLastError());
+      lbm::advance_counter_kernel<<<1, 1, 0, s.stream>>>(s.counter, 2 * pairs);
+      CK(cudaGetLastError());
+      h->last_launches += 2;
+      remaining -= 2 * pairs;
+    }
+  }
+
   if (nslab == 1 && !comm && h->use_graph) {
     Slab& s = h->slabs[0];
     while (remaining > h->chunk) {
@@ -472,8 +616,8 @@ int run_impl(lbm_lattice* h, int iters, double* av_out)
         // the north-star formulation: this step's slab total -> all ranks, right away
         Slab& s = h->slabs[0];
         const long long idx = step_no;
-        lbm::reduce_partials_kernel<<<1, 256, 0, s.stream>>>(s.partials + (long long)i * s.nblk, s.nblk,
-                                                            s.totals + idx, comm->scratch64);
+        lbm::reduce_partials_kernel<<<1, 256, 0, s.stream>>>(s.partials + (long long)i * s.np, s.np, s.nblk,
+                                                            s.nblk, s.totals + idx, comm->scratch64);
         CK(cudaGetLastError());
         CK(cudaEventRecord(comm->ev_side, s.stream));
         CK(cudaStreamWaitEvent(comm->side, comm->ev_side, 0));
@@ -488,7 +632,7 @@ int run_impl(lbm_lattice* h, int iters, double* av_out)
     if (!(comm && comm->per_step_allreduce)) {
       for (auto& s : h->slabs) {
         CK(cudaSetDevice(s.device));
-        lbm::reduce_partials_kernel<<<n, 256, 0, s.stream>>>(s.partials, s.nblk, s.totals, s.counter);
+        lbm::reduce_partials_kernel<<<n, 256, 0, s.stream>>>(s.partials, s.np, s.nblk, s.nblk, s.totals, s.counter);
         CK(cudaGetLastError());
         lbm::advance_counter_kernel<<<1, 1, 0, s.stream>>>(s.counter, n);
         CK(cudaGetLastError());
@@ -557,6 +701,7 @@ int run_impl(lbm_lattice* h, int iters, double* av_out)
   return 0;
 }
 
+
 void read_tuning(lbm_lattice* h)
 {
   const int nx = h->p.nx;
@@ -572,6 +717,8 @@ void read_tuning(lbm_lattice* h)
   h->use_graph = env_int("LBM_GRAPH", 1) != 0;
   h->use_pdl = env_int("LBM_PDL", -1) != 0;   // -1 = decide per slab size (create_slab)
   h->pad = std::max(0, env_int("LBM_PLANE_PAD", 0));
+  h->fuse2 = env_int("LBM_FUSE", 1) == 2;
+  g_fused_cfg = std::min(3, std::max(0, env_int("LBM_FUSE_CFG", 0)));
 }
 
 // device objects of one slab; obstacles_rows points at the slab's first row
@@ -600,13 +747,25 @@ int create_slab(lbm_lattice* h, Slab& s, const int* obstacles_rows, long long* f
   CK(cudaEventCreate(&s.ev_end));
   CK(cudaEventCreateWithFlags(&s.ev_step[0], cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&s.ev_step[1], cudaEventDisableTiming));
-  CK(cudaMalloc(&s.base, slab_bytes(s.ps)));
-  CK(cudaMemset(s.base, 0, slab_bytes(s.ps)));
+  CK(cudaMalloc(&s.base, slab_bytes(s.ps, nx)));
+  CK(cudaMemset(s.base, 0, slab_bytes(s.ps, nx)));
   s.buf[0] = reinterpret_cast<float*>(s.base);
   s.buf[1] = s.buf[0] + 9 * s.ps;
   s.sync = reinterpret_cast<unsigned*>(s.buf[1] + 9 * s.ps);
+  s.pse = strip_stride(nx);
+  s.strip_lo = strip_of(s.base, s.ps, nx, 0);
+  s.strip_hi = strip_of(s.base, s.ps, nx, 1);
+  s.tiles_x = (nx + lbm::F_TX - 1) / lbm::F_TX;
+  {
+    const int ty = FUSED_CFGS[g_fused_cfg].ra - 2;
+    s.tiles_y = (std::max(s.rows - 2, 0) + ty - 1) / ty;
+  }
+  {
+    const int nb_strip = ((nx / h->vec) + h->tpb - 1) / h->tpb;
+    s.np = std::max(s.nblk, s.tiles_x * s.tiles_y + 2 * nb_strip);
+  }
   CK(cudaMalloc(&s.flags, (size_t)cells));
-  CK(cudaMalloc(&s.partials, sizeof(double) * (size_t)h->chunk * s.nblk));
+  CK(cudaMalloc(&s.partials, sizeof(double) * (size_t)h->chunk * s.np));
   CK(cudaMalloc(&s.counter, sizeof(long long)));
   CK(cudaMemset(s.counter, 0, sizeof(long long)));
 
@@ -641,6 +800,11 @@ void wire_ghosts(Slab& s, int nx, char* lo_base, int lo_rows, long long lo_ps, c
       s.ghost_hi[b][i] = hi_buf + HI_PLANES[i] * hi_ps;
     }
   }
+  const long long pse = strip_stride(nx);
+  for (int i = 0; i < 3; i++) {
+    s.nb_lo[i] = strip_of(lo_base, lo_ps, nx, 1) + LO_PLANES[i] * pse + 2LL * nx;
+    s.nb_hi[i] = strip_of(hi_base, hi_ps, nx, 0) + HI_PLANES[i] * pse;
+  }
 }
 
 void set_config_string(lbm_lattice* h)
@@ -651,9 +815,9 @@ void set_config_string(lbm_lattice* h)
                                 : h->comm->in_kernel ? "ranks+ipc-peer-stores+in-kernel-ring"
                                                      : "ranks+ipc-peer-stores+wait/signal-kernels")
                              : (h->slabs.size() > 1 ? "one-process+peer-stores" : "single-gpu");
-  snprintf(cfg, sizeof cfg, "vec=%d tpb=%d chunk=%d graph=%d pdl=%d slabs=%d halo=%s%s plane_stride=%lld",
+  snprintf(cfg, sizeof cfg, "vec=%d tpb=%d chunk=%d graph=%d pdl=%d fuse=%d slabs=%d halo=%s%s plane_stride=%lld",
            h->vec, h->tpb, h->chunk, (int)(h->use_graph && h->world == 1),
-           (int)(h->use_pdl && h->world == 1), h->world, mode, red,
+           (int)(h->use_pdl && h->world == 1), fused_ok(h) ? 2 : 1, h->world, mode, red,
            h->slabs[0].ps);
   h->config = cfg;
 }

@@ -63,6 +63,12 @@ struct StepArgs {
   int            fuse_accel; // apply the NEXT step's accelerate_flow to the values being stored
   float*         ghost_lo[3];// row base receiving planes 4,7,8 of the first owned row
   float*         ghost_hi[3];// row base receiving planes 2,5,6 of the last owned row
+  // source and destination may be different objects (the fix-up of a two-step pass reads a
+  // 3-row strip and writes a slab row): destination plane stride, and the float offset of the
+  // destination (and flag) row relative to the source row; which ghost pushes this launch owns
+  long long      ps_dst;
+  long long      dst_delta;
+  int            push;       // bit 0: row 1 -> ghost_lo, bit 1: row `rows` -> ghost_hi
   double*        partials;   // [gridDim.x] per-block sums of cell speeds for this step
   // one-process-per-GPU ring ordering done by the boundary blocks themselves (null = not used):
   const unsigned* ring_in;   // [0] steps finished by my lower neighbour's top row, [1] by my upper's bottom row
@@ -231,7 +237,7 @@ lbm_step_kernel(const __grid_constant__ StepArgs A)
   float f[9][VEC];
   float v1[VEC], v3[VEC], v5[VEC], v6[VEC], v7[VEC], v8[VEC];
   float e1 = 0.f, e3 = 0.f, e5 = 0.f, e6 = 0.f, e7 = 0.f, e8 = 0.f;
-  const unsigned flags = ld_flags<VEC>(A.flags + row_mid + x);   // constant data: may precede the wait
+  const unsigned flags = ld_flags<VEC>(A.flags + row_mid + A.dst_delta + x);   // constant data: may precede the wait
   // everything below reads what the previous step wrote (and overwrites what it read)
   asm volatile("griddepcontrol.wait;" ::: "memory");
   ld_vec<VEC>(s + row_mid + x, f[0]);
@@ -296,15 +302,15 @@ lbm_step_kernel(const __grid_constant__ StepArgs A)
   }
 
   if (active) {
-    float* d = A.dst + row_mid + x;
+    float* d = A.dst + row_mid + A.dst_delta + x;
 #pragma unroll
-    for (int k = 0; k < 9; k++) st_vec<VEC>(d + k * ps, f[k]);
-    if (r == 1) {            // my south neighbour pulls 4,7,8 from this row
+    for (int k = 0; k < 9; k++) st_vec<VEC>(d + k * A.ps_dst, f[k]);
+    if (r == 1 && (A.push & 1)) {            // my south neighbour pulls 4,7,8 from this row
       st_vec<VEC>(A.ghost_lo[0] + x, f[4]);
       st_vec<VEC>(A.ghost_lo[1] + x, f[7]);
       st_vec<VEC>(A.ghost_lo[2] + x, f[8]);
     }
-    if (r == A.rows) {       // my north neighbour pulls 2,5,6 from this row
+    if (r == A.rows && (A.push & 2)) {       // my north neighbour pulls 2,5,6 from this row
       st_vec<VEC>(A.ghost_hi[0] + x, f[2]);
       st_vec<VEC>(A.ghost_hi[1] + x, f[5]);
       st_vec<VEC>(A.ghost_hi[2] + x, f[6]);
@@ -334,6 +340,216 @@ lbm_step_kernel(const __grid_constant__ StepArgs A)
 
   const double total = block_sum<TPB>(speed_sum);
   if (threadIdx.x == 0) A.partials[vb] = total;
+}
+
+// ---- two timesteps per pass (temporal blocking) ------------------------------------------------
+// One block = one tile: it pulls the populations of time t from HBM exactly as lbm_step_kernel
+// does, relaxes F_RA rows x 128 columns to time t+1 INTO SHARED MEMORY, and from there relaxes the
+// inner F_TY rows x 120 columns to time t+2, which is what it stores.  Per two lattice updates a
+// cell costs one (slightly amplified) read and one write instead of two of each; the arithmetic
+// per cell and step is the same f32-strict sequence, so the state stays bit-identical.
+//
+// Ghost depth stays 1: with ghost rows valid at time t a slab can compute t+1 on all of its rows
+// but t+2 only on rows 2..rows-1.  Rows 1 and `rows` of time t+2 need the neighbours' t+1 boundary
+// rows; the pass therefore also writes the t+1 populations of rows 1, 2, rows-1, rows into two 3-row
+// "strips" (own rows + a ghost row that the NEIGHBOUR's pass fills over NVLink), and two tiny
+// launches of lbm_step_kernel on those strips (rows = 1) finish rows 1 and `rows` and push the t+2
+// ghost rows as usual.  strip_lo rows: [neighbour's last row | my row 1 | my row 2];
+// strip_hi rows: [my row rows-1 | my row rows | neighbour's first row].
+constexpr int F_TX = 120;   // output columns per tile (30 lanes x 4)
+// tile height and block size are template parameters (RA = rows relaxed to t+1 = output rows + one
+// above and below); shared memory = 9 planes x RA rows x 32 lanes x 16 B
+constexpr int fused_smem(int ra) { return 9 * ra * 32 * 16; }
+
+struct FusedArgs {
+  const float*   src;
+  float*         dst;
+  const uint8_t* flags;
+  long long      ps;
+  int            nx, rows, tiles_x, tiles_y;
+  float          omega, a1, a2;
+  int            fuse_b;       // apply the following step's acceleration to the t+2 values
+  float*         strip_lo;     // 9 planes, stride pse, 3 rows of nx
+  float*         strip_hi;
+  long long      pse;
+  float*         nb_lo[3];     // lower neighbour's strip_hi row 2: planes 4,7,8 of my row 1 (t+1)
+  float*         nb_hi[3];     // upper neighbour's strip_lo row 0: planes 2,5,6 of my row `rows` (t+1)
+  double*        partials_a;   // [tiles] speed sums of step t+1
+  double*        partials_b;   // [tiles] speed sums of step t+2 (rows 2..rows-1)
+};
+
+// relax the 4 cells a thread holds; speeds are accumulated only when `count`
+template <bool FAST>
+__device__ __forceinline__ double relax_vec4(float (&f)[9][4], unsigned flags, float omega, float a1,
+                                             float a2, bool fuse, bool count)
+{
+  double sum = 0.0;
+  if (FAST && (flags & 0x03030303u) == 0u) {
+    // plain fluid everywhere: four independent relaxations the scheduler can interleave
+    float usq[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      float t[9];
+#pragma unroll
+      for (int k = 0; k < 9; k++) t[k] = f[k][j];
+      usq[j] = bgk_cell(t, omega);
+#pragma unroll
+      for (int k = 0; k < 9; k++) f[k][j] = t[k];
+    }
+    if (count) {
+#pragma unroll
+      for (int j = 0; j < 4; j++) if (usq[j] > 0.0f) sum += (double)__fsqrt_rn(usq[j]);
+    }
+    return sum;
+  }
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const unsigned fl = (flags >> (8 * j)) & 0xffu;
+    float t[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) t[k] = f[k][j];
+    if (fl & FLAG_OBSTACLE) {
+      swap2(t[1], t[3]); swap2(t[2], t[4]); swap2(t[5], t[7]); swap2(t[6], t[8]);
+    } else {
+      const float usq = bgk_cell(t, omega);
+      if (count && usq > 0.0f) sum += (double)__fsqrt_rn(usq);
+      if (fuse && (fl & FLAG_ACCEL)) accelerate_cell(t, a1, a2);
+    }
+#pragma unroll
+    for (int k = 0; k < 9; k++) f[k][j] = t[k];
+  }
+  return sum;
+}
+
+__device__ __forceinline__ float4 f4(const float (&v)[4]) { return make_float4(v[0], v[1], v[2], v[3]); }
+
+template <int F_TPB, int F_RA, int MINB>
+__global__ void __launch_bounds__(F_TPB, MINB)
+lbm_fused2_kernel(const __grid_constant__ FusedArgs A)
+{
+  constexpr int F_TY = F_RA - 2;
+  extern __shared__ float4 tile[];                 // [9][F_RA][32]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int bx = (int)(blockIdx.x % (unsigned)A.tiles_x), by = (int)(blockIdx.x / (unsigned)A.tiles_x);
+  const int oy0 = 2 + F_TY * by;                   // first output row (storage index)
+  const int oy1 = min(oy0 + F_TY, A.rows);         // one past the last output row (<= rows-1)
+  const int ay0 = oy0 - 1;                         // first row relaxed to t+1
+  const int nra = oy1 - oy0 + 2;
+  const int xu = F_TX * bx - 4 + 4 * lane;         // my first column before the periodic wrap
+  const int x = xu < 0 ? xu + A.nx : (xu >= A.nx ? xu - A.nx : xu);
+  const int xw = (x == 0) ? A.nx - 1 : x - 1;
+  const int xe = (x + 4 == A.nx) ? 0 : x + 4;
+  const bool mine = lane >= 1 && lane <= 30 && xu < A.nx;   // columns this tile stores / accounts for
+  const long long ps = A.ps;
+  double sum_a = 0.0, sum_b = 0.0;
+
+  // ---- step t -> t+1: rows ay0 .. ay0+nra-1, all 128 columns, into shared memory
+  for (int ar = warp; ar < nra; ar += F_TPB / 32) {
+    const int r = ay0 + ar;
+    const long long row_mid = (long long)r * A.nx;
+    const long long row_lo = row_mid - A.nx, row_hi = row_mid + A.nx;
+    const float* s = A.src;
+    const float* p1 = s + 1 * ps + row_mid; const float* p3 = s + 3 * ps + row_mid;
+    const float* p5 = s + 5 * ps + row_lo;  const float* p6 = s + 6 * ps + row_lo;
+    const float* p7 = s + 7 * ps + row_hi;  const float* p8 = s + 8 * ps + row_hi;
+    float f[9][4];
+    float v1[4], v3[4], v5[4], v6[4], v7[4], v8[4];
+    float e1 = 0.f, e3 = 0.f, e5 = 0.f, e6 = 0.f, e7 = 0.f, e8 = 0.f;
+    ld_vec<4>(s + row_mid + x, f[0]);
+    ld_vec<4>(p1 + x, v1);
+    ld_vec<4>(s + 2 * ps + row_lo + x, f[2]);
+    ld_vec<4>(p3 + x, v3);
+    ld_vec<4>(s + 4 * ps + row_hi + x, f[4]);
+    ld_vec<4>(p5 + x, v5);
+    ld_vec<4>(p6 + x, v6);
+    ld_vec<4>(p7 + x, v7);
+    ld_vec<4>(p8 + x, v8);
+    const unsigned flags = ld_flags<4>(A.flags + row_mid + x);
+    if (lane == 0)  { e1 = p1[xw]; e5 = p5[xw]; e8 = p8[xw]; }
+    if (lane == 31) { e3 = p3[xe]; e6 = p6[xe]; e7 = p7[xe]; }
+    {
+      const float l1 = __shfl_up_sync(FULL_MASK, v1[3], 1);
+      const float l5 = __shfl_up_sync(FULL_MASK, v5[3], 1);
+      const float l8 = __shfl_up_sync(FULL_MASK, v8[3], 1);
+      const float r3 = __shfl_down_sync(FULL_MASK, v3[0], 1);
+      const float r6 = __shfl_down_sync(FULL_MASK, v6[0], 1);
+      const float r7 = __shfl_down_sync(FULL_MASK, v7[0], 1);
+      f[1][0] = lane == 0 ? e1 : l1;  f[5][0] = lane == 0 ? e5 : l5;  f[8][0] = lane == 0 ? e8 : l8;
+      f[3][3] = lane == 31 ? e3 : r3; f[6][3] = lane == 31 ? e6 : r6; f[7][3] = lane == 31 ? e7 : r7;
+#pragma unroll
+      for (int i = 1; i < 4; i++) { f[1][i] = v1[i - 1]; f[5][i] = v5[i - 1]; f[8][i] = v8[i - 1]; }
+#pragma unroll
+      for (int i = 0; i < 3; i++) { f[3][i] = v3[i + 1]; f[6][i] = v6[i + 1]; f[7][i] = v7[i + 1]; }
+    }
+    // every cell of the slab is accounted for once at t+1: by the tile whose output row it is, rows
+    // 1 and `rows` (relaxed here only as halo rows) by the bottom and the top tile
+    const bool count = mine && ((ar >= 1 && ar <= nra - 2) || r == 1 || r == A.rows);
+    // step t+2 always follows inside this pass, so its acceleration is applied here
+    sum_a += relax_vec4<false>(f, flags, A.omega, A.a1, A.a2, true, count);
+#pragma unroll
+    for (int k = 0; k < 9; k++) tile[(k * F_RA + ar) * 32 + lane] = f4(f[k]);
+
+    if (mine) {   // t+1 boundary rows for the fix-up launches (own strips, neighbours' ghost rows)
+      if (r == 1) {
+#pragma unroll
+        for (int k = 0; k < 9; k++) st_vec<4>(A.strip_lo + k * A.pse + A.nx + x, f[k]);
+        st_vec<4>(A.nb_lo[0] + x, f[4]); st_vec<4>(A.nb_lo[1] + x, f[7]); st_vec<4>(A.nb_lo[2] + x, f[8]);
+      }
+      if (r == 2) {
+        st_vec<4>(A.strip_lo + 4 * A.pse + 2 * A.nx + x, f[4]);
+        st_vec<4>(A.strip_lo + 7 * A.pse + 2 * A.nx + x, f[7]);
+        st_vec<4>(A.strip_lo + 8 * A.pse + 2 * A.nx + x, f[8]);
+      }
+      if (r == A.rows - 1) {
+        st_vec<4>(A.strip_hi + 2 * A.pse + x, f[2]);
+        st_vec<4>(A.strip_hi + 5 * A.pse + x, f[5]);
+        st_vec<4>(A.strip_hi + 6 * A.pse + x, f[6]);
+      }
+      if (r == A.rows) {
+#pragma unroll
+        for (int k = 0; k < 9; k++) st_vec<4>(A.strip_hi + k * A.pse + A.nx + x, f[k]);
+        st_vec<4>(A.nb_hi[0] + x, f[2]); st_vec<4>(A.nb_hi[1] + x, f[5]); st_vec<4>(A.nb_hi[2] + x, f[6]);
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- step t+1 -> t+2: output rows from shared memory (lanes 0 and 31 only feed their neighbours)
+  for (int orow = oy0 + warp; orow < oy1; orow += F_TPB / 32) {
+    const int ar = orow - ay0;
+    const long long row_mid = (long long)orow * A.nx;
+    const unsigned flags = ld_flags<4>(A.flags + row_mid + x);
+    const float4 q0 = tile[(0 * F_RA + ar) * 32 + lane];
+    const float4 q1 = tile[(1 * F_RA + ar) * 32 + lane];
+    const float4 q3 = tile[(3 * F_RA + ar) * 32 + lane];
+    const float4 q2 = tile[(2 * F_RA + ar - 1) * 32 + lane];
+    const float4 q5 = tile[(5 * F_RA + ar - 1) * 32 + lane];
+    const float4 q6 = tile[(6 * F_RA + ar - 1) * 32 + lane];
+    const float4 q4 = tile[(4 * F_RA + ar + 1) * 32 + lane];
+    const float4 q7 = tile[(7 * F_RA + ar + 1) * 32 + lane];
+    const float4 q8 = tile[(8 * F_RA + ar + 1) * 32 + lane];
+    float f[9][4];
+    f[0][0] = q0.x; f[0][1] = q0.y; f[0][2] = q0.z; f[0][3] = q0.w;
+    f[2][0] = q2.x; f[2][1] = q2.y; f[2][2] = q2.z; f[2][3] = q2.w;
+    f[4][0] = q4.x; f[4][1] = q4.y; f[4][2] = q4.z; f[4][3] = q4.w;
+    f[1][0] = __shfl_up_sync(FULL_MASK, q1.w, 1); f[1][1] = q1.x; f[1][2] = q1.y; f[1][3] = q1.z;
+    f[5][0] = __shfl_up_sync(FULL_MASK, q5.w, 1); f[5][1] = q5.x; f[5][2] = q5.y; f[5][3] = q5.z;
+    f[8][0] = __shfl_up_sync(FULL_MASK, q8.w, 1); f[8][1] = q8.x; f[8][2] = q8.y; f[8][3] = q8.z;
+    f[3][3] = __shfl_down_sync(FULL_MASK, q3.x, 1); f[3][0] = q3.y; f[3][1] = q3.z; f[3][2] = q3.w;
+    f[6][3] = __shfl_down_sync(FULL_MASK, q6.x, 1); f[6][0] = q6.y; f[6][1] = q6.z; f[6][2] = q6.w;
+    f[7][3] = __shfl_down_sync(FULL_MASK, q7.x, 1); f[7][0] = q7.y; f[7][1] = q7.z; f[7][2] = q7.w;
+    sum_b += relax_vec4<false>(f, flags, A.omega, A.a1, A.a2, A.fuse_b != 0, mine);
+    if (mine) {
+      float* d = A.dst + row_mid + x;
+#pragma unroll
+      for (int k = 0; k < 9; k++) st_vec<4>(d + k * ps, f[k]);
+    }
+  }
+
+  const double ta = block_sum<F_TPB>(sum_a);
+  __syncthreads();
+  const double tb = block_sum<F_TPB>(sum_b);
+  if (threadIdx.x == 0) { A.partials_a[blockIdx.x] = ta; A.partials_b[blockIdx.x] = tb; }
 }
 
 // ---- small kernels ---------------------------------------------------------------------------
@@ -388,11 +604,14 @@ __global__ void init_equilibrium_kernel(float* buf, long long ps, long long cell
 // second stage of the average-velocity reduction: block s sums the nblk partials of step s in a
 // fixed order and writes the slab's speed total for that step (divided later by tot_cells).
 // `counter` holds the index of the first step of this chunk inside `totals`.
-__global__ void reduce_partials_kernel(const double* partials, int nblk, double* totals,
-                                       const long long* counter)
+// `stride` = partial slots per step; steps with an even / odd index in the chunk hold
+// count_even / count_odd valid partials (they differ only in two-step passes).
+__global__ void reduce_partials_kernel(const double* partials, int stride, int count_even, int count_odd,
+                                       double* totals, const long long* counter)
 {
   __shared__ double sm[256];
-  const double* p = partials + (long long)blockIdx.x * nblk;
+  const double* p = partials + (long long)blockIdx.x * stride;
+  const int nblk = (blockIdx.x & 1) ? count_odd : count_even;
   double v = 0.0;
   for (int i = threadIdx.x; i < nblk; i += 256) v += p[i];
   sm[threadIdx.x] = v;

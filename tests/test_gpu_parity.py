@@ -352,3 +352,60 @@ def test_executable_on_two_gpus(lbm, tmp_path):
         outs[n] = (open(d / "final_state.dat", "rb").read(), np.loadtxt(d / "av_vels.dat", usecols=[1]))
     assert outs[1][0] == outs[2][0]
     assert np.max(np.abs(outs[1][1] - outs[2][1]) / outs[1][1]) <= 1.2e-7
+
+
+# ---- two timesteps per pass (LBM_FUSE=2) --------------------------------------------------------
+FUSED_SIZES = [(128, 128), (256, 20), (1024, 12), (512, 37), (136, 9), (1000, 33), (248, 4), (2048, 70)]
+
+
+@pytest.mark.parametrize("nx,ny", FUSED_SIZES)
+@pytest.mark.parametrize("iters", [2, 7, 40])
+def test_two_step_passes_bit_exact(lbm, nx, ny, iters, monkeypatch):
+    """temporal blocking through shared-memory tiles + strip fix-ups: same arithmetic per cell and
+    step, so still bit-identical to the oracle; odd counts end with one ordinary step"""
+    monkeypatch.setenv("LBM_FUSE", "2")
+    monkeypatch.setenv("LBM_CHUNK", "8")
+    case = cases.random_case(nx, ny, seed=nx + 3 * ny, walls=(ny > 8))
+    f0 = cases.perturbed_state(case, seed=nx)
+    o = Oracle("f32b200", case)
+    f = f0.copy()
+    av = o.run(f, iters)
+    with make(lbm, case) as lat:
+        assert "fuse=2" in lat.config
+        lat.upload(f0)
+        av_gpu = lat.run(iters, f64=True)
+        assert_state_bit_exact(lat.download(), f)
+        assert np.max(np.abs(av_gpu - av) / np.abs(av)) <= 1e-12
+        av2 = o.run(f, 5)
+        av_gpu2 = lat.run(5, f64=True)          # continue: 2 passes + 1 plain step
+        assert_state_bit_exact(lat.download(), f)
+        assert np.max(np.abs(av_gpu2 - av2) / np.abs(av2)) <= 1e-12
+
+
+def test_two_step_passes_shipped_case(lbm, monkeypatch):
+    monkeypatch.setenv("LBM_FUSE", "2")
+    case = cases.shipped("128x256")             # periodic in y, accelerated row next to the seam
+    o = Oracle("f32b200", case)
+    f = o.init()
+    av = o.run(f, 501)
+    with make(lbm, case) as lat:
+        lat.init_equilibrium()
+        av_gpu = lat.run(501, f64=True)
+        assert_state_bit_exact(lat.download(), f)
+        assert np.max(np.abs(av_gpu - av) / np.abs(av)) <= 1e-12
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_two_step_passes_one_process_per_gpu(lbm, world):
+    if _gpus(lbm) < world:
+        pytest.skip("needs %d GPUs" % world)
+    import sys
+    env = dict(os.environ, LBM_FUSE="2")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+           "--master-addr", "127.0.0.1", "--master-port", str(29700 + world),
+           os.path.join(cases.ROOT, "tools", "multirank_check.py"), "--nx", "512", "--ny", "100",
+           "--steps", "41"]
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=300)
+    print(r.stdout[-600:])
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "-> OK" in r.stdout and "fuse=2" in r.stdout
