@@ -209,7 +209,7 @@ struct lbm_lattice {
   int vec = 4, tpb = 128, chunk = 128, pad = 0;
   bool use_graph = true;
   bool use_pdl = false;        // programmatic dependent launch between consecutive steps (1 GPU)
-  bool fuse2 = false;          // two timesteps per pass through shared-memory tiles (LBM_FUSE=2)
+  int fuse_mode = -1;          // LBM_FUSE: 2 = two timesteps per pass, 1 = one, -1 = by slab size
   double last_ms = 0;
   long long last_launches = 0;
   std::string config;
@@ -412,11 +412,15 @@ void drop_graphs(Slab& s)
 }
 
 // ---- two-step passes (LBM_FUSE=2) ---------------------------------------------------------------
+// Two-step passes halve the DRAM traffic but cost ~20 % more instructions and run at lower
+// occupancy: they win once a slab streams from HBM (+17 % at 16384^2, profiles/r1_tuning.md) and lose
+// when it lives in L2 (1024^2: -40 %), so "auto" turns them on from 8 M cells (0.6 GB of state) up.
 bool fused_ok(const lbm_lattice* h)
 {
-  if (!h->fuse2 || h->slabs.size() != 1 || h->vec != 4 || h->p.nx < 128 || h->slabs[0].rows < 4) return false;
+  if (h->fuse_mode == 1 || h->slabs.size() != 1 || h->vec != 4 || h->p.nx < 128 || h->slabs[0].rows < 4) return false;
   if (h->comm && (h->comm->halo != HALO_P2P || h->comm->per_step_allreduce)) return false;
-  return true;
+  if (h->fuse_mode == 2) return true;
+  return (long long)h->slabs[0].rows * h->p.nx >= (8LL << 20);
 }
 
 // t -> t+2 on rows 2..rows-1 of buffer cur^1, t+1 boundary rows into the strips (slots: 2 steps)
@@ -717,7 +721,7 @@ void read_tuning(lbm_lattice* h)
   h->use_graph = env_int("LBM_GRAPH", 1) != 0;
   h->use_pdl = env_int("LBM_PDL", -1) != 0;   // -1 = decide per slab size (create_slab)
   h->pad = std::max(0, env_int("LBM_PLANE_PAD", 0));
-  h->fuse2 = env_int("LBM_FUSE", 1) == 2;
+  h->fuse_mode = env_int("LBM_FUSE", -1);
   g_fused_cfg = std::min(3, std::max(0, env_int("LBM_FUSE_CFG", 0)));
 }
 

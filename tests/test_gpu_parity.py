@@ -200,6 +200,7 @@ def test_full_size_channel_properties(lbm):
     ob = cases.channel(nx, ny, rows=(0, ny))
     lat = lbm.Lattice(nx, ny, 0.1, 0.005, 1.85, ob)
     try:
+        assert "fuse=2" in lat.config          # HBM-streaming slab: two timesteps per pass by default
         lat.init_equilibrium()
         av = lat.run(12, f64=True)
         m = lat.macroscopic()
@@ -218,12 +219,18 @@ def test_full_size_channel_properties(lbm):
     small = cases.channel(nx, 64)
     o = Oracle("f32b200", small)
     f = o.init()
-    avo = o.run(f, 10)
-    with make(lbm, small) as lat2:
-        lat2.init_equilibrium()
-        avg = lat2.run(10, f64=True)
-        assert_state_bit_exact(lat2.download(), f)
-    assert np.max(np.abs(avg - avo) / avo) <= 1e-12
+    avo = o.run(f, 11)
+    for fuse in ("1", "2"):           # the one-step kernel and the two-step passes the big grid uses
+        os.environ["LBM_FUSE"] = fuse
+        try:
+            with make(lbm, small) as lat2:
+                assert ("fuse=%s" % fuse) in lat2.config
+                lat2.init_equilibrium()
+                avg = lat2.run(11, f64=True)
+                assert_state_bit_exact(lat2.download(), f)
+        finally:
+            del os.environ["LBM_FUSE"]
+        assert np.max(np.abs(avg - avo) / avo) <= 1e-12
 
 
 # ---- more than one GPU (skipped on a single-GPU box) -------------------------------------------
@@ -355,7 +362,8 @@ def test_executable_on_two_gpus(lbm, tmp_path):
 
 
 # ---- two timesteps per pass (LBM_FUSE=2) --------------------------------------------------------
-FUSED_SIZES = [(128, 128), (256, 20), (1024, 12), (512, 37), (136, 9), (1000, 33), (248, 4), (2048, 70)]
+FUSED_SIZES = [(128, 128), (256, 20), (1024, 12), (512, 37), (136, 9), (1000, 33), (248, 4), (2048, 70),
+               (16384, 19)]
 
 
 @pytest.mark.parametrize("nx,ny", FUSED_SIZES)
