@@ -417,10 +417,12 @@ void drop_graphs(Slab& s)
 // when it lives in L2 (1024^2: -40 %), so "auto" turns them on from 8 M cells (0.6 GB of state) up.
 bool fused_ok(const lbm_lattice* h)
 {
-  if (h->fuse_mode == 1 || h->slabs.size() != 1 || h->vec != 4 || h->p.nx < 128 || h->slabs[0].rows < 4) return false;
+  // decided from global quantities only: every rank of a ring must take the same path
+  const int min_rows = h->p.ny / h->world;
+  if (h->fuse_mode == 1 || h->slabs.size() != 1 || h->vec != 4 || h->p.nx < 128 || min_rows < 4) return false;
   if (h->comm && (h->comm->halo != HALO_P2P || h->comm->per_step_allreduce)) return false;
   if (h->fuse_mode == 2) return true;
-  return (long long)h->slabs[0].rows * h->p.nx >= (8LL << 20);
+  return (long long)min_rows * h->p.nx >= (8LL << 20);
 }
 
 // t -> t+2 on rows 2..rows-1 of buffer cur^1, t+1 boundary rows into the strips (slots: 2 steps)
@@ -465,6 +467,16 @@ int launch_fused(lbm_lattice* h, Slab& s, int cur, int fuse_b, int slot)
   for (int i = 0; i < 3; i++) { a.nb_lo[i] = s.nb_lo[i]; a.nb_hi[i] = s.nb_hi[i]; }
   a.partials_a = s.partials + (long long)slot * s.np;
   a.partials_b = s.partials + (long long)(slot + 1) * s.np;
+  if (h->comm && h->comm->in_kernel) {
+    const Comm* c = h->comm;
+    a.ring_in = s.sync;
+    a.ring_out_lo = c->peer_lo_flag;
+    a.ring_out_hi = c->peer_hi_flag;
+    a.ring_tickets = s.sync + 4;
+    a.ring_timeout = s.sync + 2;
+    a.ring_step = c->steps_done;
+    a.rot = s.tiles_x;
+  }
   const int nt = s.tiles_x * s.tiles_y;
   switch (g_fused_cfg) {
     case 1: return launch_fused_t<256, 16, 3>(a, nt, s.stream);
@@ -491,8 +503,8 @@ int launch_fixups(lbm_lattice* h, Slab& s, int cur, int fuse_b, int slot)
     a.dst_delta = hi ? (long long)(s.rows - 1) * nx : 0;
     a.push = hi ? 2 : 1;
     a.partials = s.partials + (long long)slot * s.np + ntiles + hi * nb_strip;
-    a.ring_in = nullptr;      // ordering of two-step passes is done by the wait/signal launches
-    a.rot = 0;
+    a.rot = 0;                // ring ordering (if done in the kernel): this strip's side only, see `push`
+    a.nb_lo = a.nb_hi = nb_strip;
     CK(launch_step(h->vec, h->tpb, a, nb_strip, s.stream));
   }
   return 0;
@@ -531,27 +543,28 @@ int run_impl(lbm_lattice* h, int iters, double* av_out)
       const int pairs = std::min(remaining / 2, h->chunk / 2);
       for (int j = 0; j < pairs; j++) {
         const int fuse_b = (remaining - 2 * j - 2) > 0;
-        if (comm) {
+        const bool launches_order = comm && !comm->in_kernel;   // else the kernels order themselves
+        if (launches_order) {
           lbm::wait_neighbours_kernel<<<1, 2, 0, s.stream>>>(s.sync, comm->steps_done, s.sync + 2);
           CK(cudaGetLastError());
         }
         if (launch_fused(h, s, cur, fuse_b, 2 * j)) return 1;
-        if (comm) {   // my t+1 boundary rows are in the neighbours' strips; wait for theirs
+        if (launches_order) {   // my t+1 boundary rows are in the neighbours' strips; wait for theirs
           lbm::signal_neighbours_kernel<<<1, 2, 0, s.stream>>>(comm->peer_lo_flag, comm->peer_hi_flag,
                                                                comm->steps_done + 1);
           CK(cudaGetLastError());
-          comm->steps_done++;
-          lbm::wait_neighbours_kernel<<<1, 2, 0, s.stream>>>(s.sync, comm->steps_done, s.sync + 2);
+          lbm::wait_neighbours_kernel<<<1, 2, 0, s.stream>>>(s.sync, comm->steps_done + 1, s.sync + 2);
           CK(cudaGetLastError());
         }
+        if (comm) comm->steps_done++;
         if (launch_fixups(h, s, cur, fuse_b, 2 * j + 1)) return 1;
-        if (comm) {
+        if (launches_order) {
           lbm::signal_neighbours_kernel<<<1, 2, 0, s.stream>>>(comm->peer_lo_flag, comm->peer_hi_flag,
                                                                comm->steps_done + 1);
           CK(cudaGetLastError());
-          comm->steps_done++;
         }
-        h->last_launches += comm ? 7 : 3;
+        if (comm) comm->steps_done++;
+        h->last_launches += launches_order ? 7 : 3;
         cur ^= 1;
       }
       lbm::reduce_partials_kernel<<<2 * pairs, 256, 0, s.stream>>>(s.partials, s.np, ntiles,

@@ -199,8 +199,8 @@ lbm_step_kernel(const __grid_constant__ StepArgs A)
     // my ghost row (my input) have landed and it no longer reads the ghost row I will overwrite.
     const unsigned first = vb * TPB;
     const unsigned last = min(first + TPB, (unsigned)A.nvec) - 1u;
-    ring_lo = first < (unsigned)A.nxv;
-    ring_hi = last >= (unsigned)(A.rows - 1) * (unsigned)A.nxv;
+    ring_lo = first < (unsigned)A.nxv && (A.push & 1);      // a strip launch owns one side only
+    ring_hi = last >= (unsigned)(A.rows - 1) * (unsigned)A.nxv && (A.push & 2);
     if (ring_lo || ring_hi) {
       if (threadIdx.x == 0) {
         if (ring_lo) spin_until(A.ring_in + 0, A.ring_step, A.ring_timeout);
@@ -376,6 +376,14 @@ struct FusedArgs {
   float*         nb_hi[3];     // upper neighbour's strip_lo row 0: planes 2,5,6 of my row `rows` (t+1)
   double*        partials_a;   // [tiles] speed sums of step t+1
   double*        partials_b;   // [tiles] speed sums of step t+2 (rows 2..rows-1)
+  // ring ordering by the bottom / top tiles themselves (null = ordered by separate launches)
+  const unsigned* ring_in;
+  unsigned*      ring_out_lo;
+  unsigned*      ring_out_hi;
+  unsigned*      ring_tickets;
+  unsigned*      ring_timeout;
+  unsigned       ring_step;
+  int            rot;          // tiles rotated to the front of the grid (the top tile row)
 };
 
 // relax the 4 cells a thread holds; speeds are accumulated only when `count`
@@ -430,7 +438,25 @@ lbm_fused2_kernel(const __grid_constant__ FusedArgs A)
   constexpr int F_TY = F_RA - 2;
   extern __shared__ float4 tile[];                 // [9][F_RA][32]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int bx = (int)(blockIdx.x % (unsigned)A.tiles_x), by = (int)(blockIdx.x / (unsigned)A.tiles_x);
+  // the top row of tiles is rotated to the front of the grid, the bottom row follows: both write the
+  // t+1 boundary rows the neighbours' fix-ups need, so those are on the wire first
+  const unsigned vb = A.rot == 0 ? blockIdx.x
+                      : (blockIdx.x < (unsigned)A.rot ? gridDim.x - A.rot + blockIdx.x : blockIdx.x - A.rot);
+  const int bx = (int)(vb % (unsigned)A.tiles_x), by = (int)(vb / (unsigned)A.tiles_x);
+  bool ring_lo = false, ring_hi = false;
+  if (A.ring_in != nullptr) {
+    // before this pass the neighbour's fix-up of the previous pass must be done: it wrote my ghost
+    // row (input of the bottom / top tiles) and has read the strip row those tiles overwrite
+    ring_lo = by == 0;
+    ring_hi = by == A.tiles_y - 1;
+    if (ring_lo || ring_hi) {
+      if (threadIdx.x == 0) {
+        if (ring_lo) spin_until(A.ring_in + 0, A.ring_step, A.ring_timeout);
+        if (ring_hi) spin_until(A.ring_in + 1, A.ring_step, A.ring_timeout);
+      }
+      __syncthreads();
+    }
+  }
   const int oy0 = 2 + F_TY * by;                   // first output row (storage index)
   const int oy1 = min(oy0 + F_TY, A.rows);         // one past the last output row (<= rows-1)
   const int ay0 = oy0 - 1;                         // first row relaxed to t+1
@@ -546,10 +572,28 @@ lbm_fused2_kernel(const __grid_constant__ FusedArgs A)
     }
   }
 
+  if (ring_lo || ring_hi) {
+    // my t+1 boundary rows are in the neighbour's strip: publish "phase ring_step done" per side
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      if (ring_lo && atomicAdd(A.ring_tickets + 0, 1u) == (unsigned)A.tiles_x - 1u) {
+        A.ring_tickets[0] = 0u;
+        __threadfence_system();
+        st_release_sys(A.ring_out_lo, A.ring_step + 1u);
+      }
+      if (ring_hi && atomicAdd(A.ring_tickets + 1, 1u) == (unsigned)A.tiles_x - 1u) {
+        A.ring_tickets[1] = 0u;
+        __threadfence_system();
+        st_release_sys(A.ring_out_hi, A.ring_step + 1u);
+      }
+    }
+  }
+
   const double ta = block_sum<F_TPB>(sum_a);
   __syncthreads();
   const double tb = block_sum<F_TPB>(sum_b);
-  if (threadIdx.x == 0) { A.partials_a[blockIdx.x] = ta; A.partials_b[blockIdx.x] = tb; }
+  if (threadIdx.x == 0) { A.partials_a[vb] = ta; A.partials_b[vb] = tb; }
 }
 
 // ---- small kernels ---------------------------------------------------------------------------
