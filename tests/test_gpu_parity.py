@@ -238,6 +238,15 @@ def _gpus(lbm):
     return lbm.device_count()
 
 
+def _free_port():
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
 @pytest.mark.parametrize("ngpus", [2, 4, 8])
 def test_one_process_row_slabs_bit_exact(lbm, ngpus):
     """lbm_create(ngpus=N): slabs on N GPUs of this process, halos by NVLink peer stores"""
@@ -277,9 +286,8 @@ def test_one_process_per_gpu_bit_exact(lbm, world, halo, nx):
         env["LBM_RING"] = "kernels"
     if halo == "p2p-allreduce":
         env["LBM_REDUCE"] = "step"      # one 8-byte ncclAllReduce per timestep (north-star wording)
-    port = 29600 + world * 10 + ["p2p", "p2p-kernels", "nccl", "p2p-allreduce"].index(halo) + (4 if nx == 516 else 0)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
-           "--master-addr", "127.0.0.1", "--master-port", str(port),
+           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
            os.path.join(cases.ROOT, "tools", "multirank_check.py"), "--nx", str(nx), "--ny", "100",
            "--steps", "40"]
     r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=300)
@@ -410,7 +418,7 @@ def test_two_step_passes_one_process_per_gpu(lbm, world):
     import sys
     env = dict(os.environ, LBM_FUSE="2")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
-           "--master-addr", "127.0.0.1", "--master-port", str(29700 + world),
+           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
            os.path.join(cases.ROOT, "tools", "multirank_check.py"), "--nx", "512", "--ny", "100",
            "--steps", "41"]
     r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=300)
