@@ -428,8 +428,9 @@ bool fused_ok(const lbm_lattice* h)
 // t -> t+2 on rows 2..rows-1 of buffer cur^1, t+1 boundary rows into the strips (slots: 2 steps)
 // tile shapes of the two-step kernel: {threads, rows relaxed to t+1, min blocks per SM}
 struct FusedCfg { int tpb, ra, minb; };
-// {256,16,2} measured best on B200 (profiles/r1_tuning.md section 7): 116 registers, 2 blocks per SM
-const FusedCfg FUSED_CFGS[] = {{256, 16, 2}, {256, 16, 3}, {256, 24, 2}, {384, 24, 2}};
+// {224,14,3} measured best on B200 (profiles/r1_tuning.md section 7): 7 warps x 2 rows, 64.5 KB of shared
+// memory, 80 registers, 3 blocks per SM (193 KB of shared memory in use leaves the L1 some room)
+const FusedCfg FUSED_CFGS[] = {{224, 14, 3}, {256, 16, 2}, {288, 18, 2}, {320, 20, 2}, {192, 12, 3}, {160, 10, 4}};
 int g_fused_cfg = 0;
 
 template <int TPB, int RA, int MINB>
@@ -479,10 +480,12 @@ int launch_fused(lbm_lattice* h, Slab& s, int cur, int fuse_b, int slot)
   }
   const int nt = s.tiles_x * s.tiles_y;
   switch (g_fused_cfg) {
-    case 1: return launch_fused_t<256, 16, 3>(a, nt, s.stream);
-    case 2: return launch_fused_t<256, 24, 2>(a, nt, s.stream);
-    case 3: return launch_fused_t<384, 24, 2>(a, nt, s.stream);
-    default: return launch_fused_t<256, 16, 2>(a, nt, s.stream);
+    case 1: return launch_fused_t<256, 16, 2>(a, nt, s.stream);
+    case 2: return launch_fused_t<288, 18, 2>(a, nt, s.stream);
+    case 3: return launch_fused_t<320, 20, 2>(a, nt, s.stream);
+    case 4: return launch_fused_t<192, 12, 3>(a, nt, s.stream);
+    case 5: return launch_fused_t<160, 10, 4>(a, nt, s.stream);
+    default: return launch_fused_t<224, 14, 3>(a, nt, s.stream);
   }
 }
 
@@ -735,7 +738,7 @@ void read_tuning(lbm_lattice* h)
   h->use_pdl = env_int("LBM_PDL", -1) != 0;   // -1 = decide per slab size (create_slab)
   h->pad = std::max(0, env_int("LBM_PLANE_PAD", 0));
   h->fuse_mode = env_int("LBM_FUSE", -1);
-  g_fused_cfg = std::min(3, std::max(0, env_int("LBM_FUSE_CFG", 0)));
+  g_fused_cfg = std::min(5, std::max(0, env_int("LBM_FUSE_CFG", 0)));
 }
 
 // device objects of one slab; obstacles_rows points at the slab's first row

@@ -345,7 +345,7 @@ lbm_step_kernel(const __grid_constant__ StepArgs A)
 // ---- two timesteps per pass (temporal blocking) ------------------------------------------------
 // One block = one tile: it pulls the populations of time t from HBM exactly as lbm_step_kernel
 // does, relaxes F_RA rows x 128 columns to time t+1 INTO SHARED MEMORY, and from there relaxes the
-// inner F_TY rows x 120 columns to time t+2, which is what it stores.  Per two lattice updates a
+// inner F_RA-2 rows x 120 columns to time t+2, which is what it stores (default: 7 warps, F_RA = 14).  Per two lattice updates a
 // cell costs one (slightly amplified) read and one write instead of two of each; the arithmetic
 // per cell and step is the same f32-strict sequence, so the state stays bit-identical.
 //
