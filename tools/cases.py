@@ -108,3 +108,27 @@ def perturbed_state(case, seed, amp=0.05):
     f = case.initial_state().astype(np.float64)
     f *= 1.0 + amp * (rng.random(f.shape) - 0.5)
     return f.astype(np.float32)
+
+
+def _main():
+    """python tools/cases.py <shipped-name | NXxNY> <outdir> [--iters N]
+    writes input_<name>.params / obstacles_<name>.dat in the reference's text formats: one of the
+    four shipped cases (rebuilt from tests/golden/) or the seeded synthetic channel of that size."""
+    import argparse
+    ap = argparse.ArgumentParser(description=_main.__doc__)
+    ap.add_argument("case")
+    ap.add_argument("outdir")
+    ap.add_argument("--iters", type=int, default=None)
+    a = ap.parse_args()
+    if a.case in SHIPPED:
+        c = shipped(a.case)
+    else:
+        nx, ny = (int(v) for v in a.case.lower().split("x"))
+        c = channel(nx, ny)
+    pf, of = c.write(a.outdir, iters=a.iters)
+    print(pf)
+    print(of)
+
+
+if __name__ == "__main__":
+    _main()
