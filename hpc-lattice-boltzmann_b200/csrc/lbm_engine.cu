@@ -436,11 +436,14 @@ int g_fused_cfg = 0;
 template <int TPB, int RA, int MINB>
 int launch_fused_t(const lbm::FusedArgs& a, int ntiles, cudaStream_t st)
 {
-  static bool configured = false;
-  if (!configured) {
+  // the opt-in to > 48 KB of dynamic shared memory is a per-device function attribute
+  static bool configured[64] = {};
+  int dev = 0;
+  CK(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && !configured[dev]) {
     CK(cudaFuncSetAttribute(lbm::lbm_fused2_kernel<TPB, RA, MINB>,
                             cudaFuncAttributeMaxDynamicSharedMemorySize, lbm::fused_smem(RA)));
-    configured = true;
+    configured[dev] = true;
   }
   lbm::lbm_fused2_kernel<TPB, RA, MINB><<<ntiles, TPB, lbm::fused_smem(RA), st>>>(a);
   CK(cudaGetLastError());
