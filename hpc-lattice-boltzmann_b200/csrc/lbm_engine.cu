@@ -1,6 +1,6 @@
 // lbm_engine.cu -- host side of the C ABI in include/lbm_b200.h: owns the device memory, streams,
-// CUDA graphs, the slab decomposition and the inter-GPU plumbing, and launches the kernels of
-// lbm_kernels.cuh.
+// CUDA graphs, TMA descriptors, the slab decomposition and the inter-GPU plumbing, and launches the
+// kernels of lbm_kernels.cuh / lbm_stream.cuh.
 //
 // What it replaces in the reference (d2q9-bgk.c): the t_ocl object bundle (:35-67), its creation
 // (:642-780), upload (:159-201), the `for tt` loop with its buffer ping-pong (:203-234),
@@ -8,23 +8,32 @@
 // 4*nx*ny-byte read-back + serial host sum (:408-423), download (:237-272) and release (:803-809).
 //
 // Design notes
-//  * A lattice is a ring of row slabs, one per GPU.  Slab storage has a ghost row below and above;
-//    the step kernel stores boundary-row outputs straight into the neighbour's ghost rows: its own
-//    ghost rows when the ring has one member, peer pointers over NVLink otherwise (direct peer
-//    access when one process drives all GPUs, CUDA-IPC mappings when there is one process per GPU).
-//    Steps on different slabs are ordered only against their two ring neighbours -- by stream
-//    events inside one process, by release/acquire counters in peer memory across processes --
-//    never against the host.  LBM_HALO=nccl switches the multi-process halo to ncclSend/ncclRecv.
+//  * A lattice is a ring of row slabs, one per GPU.  Slab storage has GHOST (4) ghost rows below and
+//    above the owned rows, all nine planes, plus the obstacle flags of those rows: copies of the
+//    neighbouring slab's boundary rows (the slab's own opposite edge when the ring has one member,
+//    which is how the y-periodic wrap works).  Whoever computes a boundary row also stores it into
+//    the neighbour's ghost zone -- a peer pointer over NVLink when there are several GPUs (direct
+//    peer access when one process drives all GPUs, CUDA-IPC mappings when there is one process per
+//    GPU).  Slabs are ordered only against their two ring neighbours, by release/acquire counters
+//    that the boundary blocks of the kernels themselves wait on and publish; never against the
+//    host, and with no collective on the data path.  LBM_HALO=nccl (one process per GPU, one-step
+//    kernel) is the library-only contrast.
+//  * Time loop: slabs that stream from HBM advance S timesteps per launch with the TMA/mbarrier
+//    streaming kernel (lbm_stream.cuh); small or odd-shaped slabs, and the last iters mod S steps,
+//    use the one-step kernel (lbm_kernels.cuh).
 //  * Between API calls the resident state is always the reference's canonical post-step state.
 //    Inside lbm_run the inflow acceleration of step t+1 is folded into the store epilogue of step t;
 //    the first step of a run is preceded by a stand-alone accelerate kernel and the last step of a
-//    run does not pre-accelerate.
+//    run does not pre-accelerate.  Every run starts by refreshing the ghost zones.
 //  * The average-velocity reduction never leaves the device during a run: per-block double sums per
 //    step, reduced per chunk of steps by a second kernel into a per-step totals array.  After the
-//    last step the per-slab totals are combined in slab order (all-gathered first when the slabs
-//    live in different processes), so the result does not depend on timing.
-//  * On one GPU whole chunks of steps are replayed from a CUDA graph to take the launch overhead
-//    out of small grids.
+//    last step the per-slab totals are combined in slab order, so the result does not depend on
+//    timing.  LBM_REDUCE=step: the last block of every launch reduces the step's partials and
+//    pushes the slab total to every rank over NVLink -- the north-star's per-step allreduce, done by
+//    the step kernel itself.
+//  * On one GPU whole chunks of one-step launches are replayed from a CUDA graph to take the launch
+//    overhead out of small grids.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <nccl.h>
@@ -39,6 +48,7 @@
 
 #include "../../include/lbm_b200.h"
 #include "lbm_kernels.cuh"
+#include "lbm_stream.cuh"
 
 namespace {
 
@@ -69,9 +79,17 @@ int env_int(const char* name, int dflt)
   return (v && *v) ? atoi(v) : dflt;
 }
 
+bool env_is(const char* name, const char* value)
+{
+  const char* v = getenv(name);
+  return v && !strcmp(v, value);
+}
+
 // ---- NCCL, bound at run time ------------------------------------------------------------------
 // dlopen by soname: inside a PyTorch process this resolves to the libnccl.so.2 torch already
-// loaded, in the plain C program to the system one.  Only the one-process-per-GPU mode needs it.
+// loaded, in the plain C program to the system one.  Only the one-process-per-GPU mode needs it,
+// and only for set-up (unique id -> communicator, IPC handle exchange) and barriers between API
+// calls; the time loop itself uses NCCL only with LBM_HALO=nccl.
 struct NcclApi {
   void* so = nullptr;
   ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
@@ -119,58 +137,96 @@ NcclApi* nccl_api()
                   nccl_api()->GetErrorString(r_));                                            \
   } while (0)
 
+// ---- TMA descriptors: cuTensorMapEncodeTiled through the runtime's driver entry point (the
+// library does not link libcuda) ----------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn()
+{
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (tried) return fn;
+  tried = true;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+      q == cudaDriverEntryPointSuccess)
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  else
+    cudaGetLastError();
+  return fn;
+}
+
 enum { HALO_P2P = 0, HALO_NCCL = 1 };
+constexpr int G = lbm::GHOST;
+constexpr int MAX_WORLD = 64;
 
 // one-process-per-GPU plumbing of a slab
 struct Comm {
   ncclComm_t nccl = nullptr;
   int rank = 0, world = 1;
   int halo = HALO_P2P;
-  void* peer_lo = nullptr;       // IPC mapping of the lower neighbour's slab allocation
-  void* peer_hi = nullptr;       // ... upper neighbour's (same mapping when world == 2)
-  unsigned* peer_lo_flag = nullptr;   // lower neighbour's "my upper neighbour has done N steps"
-  unsigned* peer_hi_flag = nullptr;   // upper neighbour's "my lower neighbour has done N steps"
-  unsigned steps_done = 0;       // steps completed since creation (all ranks advance together)
+  std::vector<void*> peers;      // IPC mappings of every other rank's slab allocation (peers[rank] = null)
   float* dummy_ghost = nullptr;  // NCCL halo: the kernel's ghost stores go nowhere useful
   long long* scratch64 = nullptr;
   bool ready = false;            // fully attached: destroy may run its closing barrier
-  bool in_kernel = false;        // ring ordering done by the step kernel's boundary blocks
-  // LBM_REDUCE=step: one 8-byte ncclAllReduce per timestep (on a side stream, so the next step
-  // does not wait for it) instead of one all-gather of the per-step totals after the run
-  bool per_step_allreduce = false;
-  cudaStream_t side = nullptr;
-  cudaEvent_t ev_side = nullptr;
-  double* step_sums = nullptr;
-  long long step_sums_cap = 0;
 };
+
+// tile shapes of the streaming kernel: {timesteps per pass, warps (= rows per batch) per group,
+// TMA stages, blocks per SM}
+struct StreamCfg { int s, nw, k0, minb; };
+const StreamCfg STREAM_CFGS[] = {
+    {2, 4, 3, 2},   // 0: 288 threads, 102 KB: two blocks per SM
+    {3, 6, 3, 1},   // 1: 608 threads, 213 KB
+    {2, 8, 3, 1},   // 2: 544 threads, 194 KB
+    {4, 4, 2, 1},   // 3: 544 threads, 176 KB
+    {2, 3, 2, 3},   // 4: 224 threads, 65 KB: three blocks per SM
+    {1, 4, 4, 3},   // 5: one step per pass (TMA flavour of the one-step kernel), 74 KB
+    {3, 4, 2, 1},   // 6: 416 threads, 130 KB
+};
+constexpr int N_STREAM_CFGS = sizeof(STREAM_CFGS) / sizeof(STREAM_CFGS[0]);
 
 struct Slab {
   int        device = 0;
   int        rank = 0;        // position in the ring
   int        y0 = 0, rows = 0;
   long long  ps = 0;          // plane stride (floats)
-  char*      base = nullptr;  // one allocation: buffer 0 | buffer 1 | sync words
+  char*      base = nullptr;  // one allocation: buffer 0 | buffer 1 | 256 B of sync words | flags
   float*     buf[2] = {nullptr, nullptr};
-  unsigned*  sync = nullptr;  // [0] steps done by my lower neighbour, [1] by my upper, [2] timeout
-  float*     strip_lo = nullptr;   // two-step passes: t+1 rows [lower neighbour's last | my 1 | my 2]
-  float*     strip_hi = nullptr;   //                           [my rows-1 | my rows | upper neighbour's first]
-  long long  pse = 0;              // strip plane stride (floats)
-  float*     nb_lo[3] = {};        // lower neighbour's strip_hi row 2, planes 4,7,8
-  float*     nb_hi[3] = {};        // upper neighbour's strip_lo row 0, planes 2,5,6
-  int        np = 0;               // partial-sum slots per step
-  int        tiles_x = 0, tiles_y = 0;
+  // sync words: [0] phases finished by my lower neighbour's top edge, [1] by my upper neighbour's
+  // bottom edge, [2] timeout flag, [4] [5] [6] tickets (lo edge, hi edge, whole-grid launches)
+  unsigned*  sync = nullptr;
   uint8_t*   flags = nullptr;
-  double*    partials = nullptr;   // [chunk][nblk]
+  // ring neighbours as seen from this slab's device
+  char*      lo_base = nullptr;
+  char*      hi_base = nullptr;
+  int        lo_rows = 0;
+  long long  lo_ps = 0, hi_ps = 0;
+  unsigned*  ring_out_lo = nullptr;   // lower neighbour's sync[1]
+  unsigned*  ring_out_hi = nullptr;   // upper neighbour's sync[0]
+  float*     ghost_lo[2][3] = {};  // one-step kernel: [buffer][plane 4,7,8] nearest ghost row above the lower neighbour
+  float*     ghost_hi[2][3] = {};  //                  [buffer][plane 2,5,6] nearest ghost row below the upper neighbour
+  float*     gz_lo[2] = {};        // plane 0 of the lower neighbour's upper ghost zone, per buffer
+  float*     gz_hi[2] = {};        // plane 0 of the upper neighbour's lower ghost zone
+  // LBM_REDUCE=step: every rank's per-step slab totals, [world][cap] doubles in each slab; peers' copies
+  double*    allred = nullptr;
+  double*    allred_peer[MAX_WORLD] = {};
+  long long  allred_cap = 0;
+  int        np = 0;               // partial-sum slots per step
+  int        tiles_x = 0, tiles_y = 0, tile_h = 0;
+  CUtensorMap tm_state, tm_flags;
+  double*    partials = nullptr;   // [chunk][np]
   double*    totals = nullptr;     // [totals_cap] per-step speed totals of this slab
   long long* counter = nullptr;
   long long  totals_cap = 0;
   int        nblk = 0;
   long long  nvec = 0;
+  float*     macro = nullptr;      // lbm_macroscopic scratch (4 planes), allocated on first use
   cudaStream_t stream = nullptr;
   cudaEvent_t  ev_begin = nullptr, ev_end = nullptr;
-  cudaEvent_t  ev_step[2] = {nullptr, nullptr};
-  float*     ghost_lo[2][3] = {};  // [buffer][plane 4,7,8] destination of my first row
-  float*     ghost_hi[2][3] = {};  // [buffer][plane 2,5,6] destination of my last row
   cudaGraphExec_t graph[2] = {nullptr, nullptr};
   bool       owns_accel_row = false;
   int        accel_row = 0;        // storage row of global row ny-2
@@ -181,19 +237,17 @@ const int HI_PLANES[3] = {2, 5, 6};   // pulled by the row above (kernels.cl:92,
 
 long long plane_stride(int rows, int nx, int pad)
 {
-  const long long cells = (long long)(rows + 2) * nx;
+  const long long cells = (long long)(rows + 2 * G) * nx;
   return ((cells + 31) / 32) * 32 + ((long long)pad / 32) * 32;
 }
 
-long long strip_stride(int nx) { return ((3LL * nx + 31) / 32) * 32; }
+size_t flags_bytes(int rows, int nx) { return (((size_t)(rows + 2 * G) * nx + 255) / 256) * 256; }
 
-// buffer 0 | buffer 1 | 256 B of sync words | strip_lo | strip_hi
-size_t slab_bytes(long long ps, int nx) { return sizeof(float) * (18 * (size_t)ps + 64 + 18 * (size_t)strip_stride(nx)); }
-
-float* strip_of(char* base, long long ps, int nx, int hi)
-{
-  return reinterpret_cast<float*>(base) + 18 * ps + 64 + (hi ? 9 * strip_stride(nx) : 0);
-}
+// buffer 0 | buffer 1 | 256 B of sync words | flags
+size_t slab_bytes(long long ps, int rows, int nx) { return sizeof(float) * 18 * (size_t)ps + 256 + flags_bytes(rows, nx); }
+float* buf_of(char* base, long long ps, int b) { return reinterpret_cast<float*>(base) + (long long)b * 9 * ps; }
+unsigned* sync_of(char* base, long long ps) { return reinterpret_cast<unsigned*>(reinterpret_cast<float*>(base) + 18 * ps); }
+uint8_t* flags_of(char* base, long long ps) { return reinterpret_cast<uint8_t*>(base) + sizeof(float) * 18 * (size_t)ps + 256; }
 
 }  // namespace
 
@@ -209,7 +263,15 @@ struct lbm_lattice {
   int vec = 4, tpb = 128, chunk = 128, pad = 0;
   bool use_graph = true;
   bool use_pdl = false;        // programmatic dependent launch between consecutive steps (1 GPU)
-  int fuse_mode = -1;          // LBM_FUSE: 2 = two timesteps per pass, 1 = one, -1 = by slab size
+  int fuse_mode = -1;          // LBM_FUSE: S >= 2 timesteps per pass, 1 = one-step kernel only, -1 = by slab size
+  int stream_cfg = 0;          // index into STREAM_CFGS (fixed at create: tiles and TMA boxes depend on it)
+  int tile_h_max = 0;          // LBM_TILE_H: upper bound of the tile height (0 = default)
+  bool ring = false;           // several slabs ordered by release/acquire counters in peer memory
+  bool ring_in_kernel = false; // one-step kernel: counters handled by its boundary blocks (else wait/signal launches)
+  bool reduce_per_step = false;// LBM_REDUCE=step
+  bool stall_test = false;     // LBM_TEST_RING_STALL: this rank never publishes (negative test of the time-out)
+  unsigned phase = 0;          // ring phases completed since creation (all slabs advance together)
+  bool poisoned = false;       // a run failed half-way: the ring counters are out of step
   double last_ms = 0;
   long long last_launches = 0;
   std::string config;
@@ -218,6 +280,19 @@ struct lbm_lattice {
 namespace {
 
 using lbm::StepArgs;
+using lbm::StreamArgs;
+
+constexpr int ALLRED_CAP = 4096;     // per-step totals kept per rank between two drains (LBM_REDUCE=step)
+
+double* allred_of(char* base, long long ps, int rows, int nx)
+{
+  return reinterpret_cast<double*>(reinterpret_cast<char*>(flags_of(base, ps)) + flags_bytes(rows, nx));
+}
+
+size_t slab_bytes_total(long long ps, int rows, int nx, int world)
+{
+  return slab_bytes(ps, rows, nx) + sizeof(double) * (size_t)ALLRED_CAP * (size_t)world;
+}
 
 template <int VEC, int TPB>
 cudaError_t launch_step_t(const StepArgs& a, int nblk, cudaStream_t st, bool pdl)
@@ -249,12 +324,26 @@ cudaError_t launch_step(int vec, int tpb, const StepArgs& a, int nblk, cudaStrea
   return cudaErrorInvalidValue;
 }
 
-StepArgs make_args(const lbm_lattice* h, const Slab& s, int cur, int fuse, int slot)
+void fill_reduce(const lbm_lattice* h, const Slab& s, lbm::StepReduce& r, long long step_index)
+{
+  r = lbm::StepReduce{};
+  if (!h->reduce_per_step) return;
+  r.world = h->world;
+  r.rank = s.rank;
+  r.cap = ALLRED_CAP;
+  r.slot = (int)(step_index % ALLRED_CAP);
+  r.ticket = s.sync + 7;
+  for (int k = 0; k < h->world; k++) r.peer[k] = s.allred_peer[k];
+}
+
+// the one-step kernel works on a view of the slab whose row 0 is the nearest lower ghost row
+StepArgs make_args(const lbm_lattice* h, const Slab& s, int cur, int fuse, int slot, long long step_index)
 {
   StepArgs a{};
-  a.src = s.buf[cur];
-  a.dst = s.buf[cur ^ 1];
-  a.flags = s.flags;
+  const long long view = (long long)(G - 1) * h->p.nx;
+  a.src = s.buf[cur] + view;
+  a.dst = s.buf[cur ^ 1] + view;
+  a.flags = s.flags + view;
   a.ps = s.ps;
   a.nvec = s.nvec;
   a.nx = h->p.nx;
@@ -276,22 +365,19 @@ StepArgs make_args(const lbm_lattice* h, const Slab& s, int cur, int fuse, int s
     a.ghost_hi[i] = s.ghost_hi[cur ^ 1][i];
   }
   a.partials = s.partials + (long long)slot * s.np;
-  a.ps_dst = s.ps;
-  a.dst_delta = 0;
-  a.push = 3;
-  if (h->comm && h->comm->halo == HALO_P2P && h->comm->in_kernel) {
-    const Comm* c = h->comm;
+  if (h->ring && h->ring_in_kernel) {
     const long long last_row_first_item = (long long)(s.rows - 1) * a.nxv;
     a.ring_in = s.sync;
-    a.ring_out_lo = c->peer_lo_flag;
-    a.ring_out_hi = c->peer_hi_flag;
+    a.ring_out_lo = h->stall_test ? s.sync + 8 : s.ring_out_lo;
+    a.ring_out_hi = h->stall_test ? s.sync + 8 : s.ring_out_hi;
     a.ring_tickets = s.sync + 4;
     a.ring_timeout = s.sync + 2;
-    a.ring_step = c->steps_done;
+    a.ring_step = h->phase;
     a.nb_hi = s.nblk - (int)(last_row_first_item / h->tpb);
     a.nb_lo = (a.nxv + h->tpb - 1) / h->tpb;
     a.rot = a.nb_hi;
   }
+  fill_reduce(h, s, a.red, step_index);
   return a;
 }
 
@@ -299,9 +385,28 @@ int launch_accelerate(lbm_lattice* h, Slab& s, int cur)
 {
   if (!s.owns_accel_row) return 0;
   const int nx = h->p.nx;
-  lbm::accelerate_row_kernel<<<(nx + 255) / 256, 256, 0, s.stream>>>(
-      s.buf[cur], s.flags, s.ps, nx, s.accel_row, s.rows, h->a1, h->a2, s.ghost_lo[cur][1],
-      s.ghost_lo[cur][2], s.ghost_hi[cur][1], s.ghost_hi[cur][2]);
+  lbm::accelerate_row_kernel<<<(nx + 255) / 256, 256, 0, s.stream>>>(s.buf[cur], s.flags, s.ps, nx, s.accel_row,
+                                                                    h->a1, h->a2);
+  CK(cudaGetLastError());
+  h->last_launches++;
+  return 0;
+}
+
+// ghost zones of buffer `cur` <- the neighbours' boundary rows; with a ring: publishes phase + 1
+int launch_refresh(lbm_lattice* h, Slab& s, int cur)
+{
+  const int nx = h->p.nx;
+  unsigned* out_lo = h->ring ? (h->stall_test ? s.sync + 8 : s.ring_out_lo) : nullptr;
+  unsigned* out_hi = h->ring ? (h->stall_test ? s.sync + 8 : s.ring_out_hi) : nullptr;
+  const long long items = 18LL * G * nx;
+  const int nb = (int)std::min<long long>((items / 4 + 255) / 256, 148LL * 4);
+  if (nx % 4 == 0)
+    lbm::ghost_refresh_kernel<<<nb, 256, 0, s.stream>>>(s.buf[cur], s.ps, nx, s.rows, s.gz_lo[cur], s.lo_ps,
+                                                       s.gz_hi[cur], s.hi_ps, out_lo, out_hi, s.sync + 4, h->phase);
+  else
+    lbm::ghost_refresh_scalar_kernel<<<nb, 256, 0, s.stream>>>(s.buf[cur], s.ps, nx, s.rows, s.gz_lo[cur], s.lo_ps,
+                                                              s.gz_hi[cur], s.hi_ps, out_lo, out_hi, s.sync + 4,
+                                                              h->phase);
   CK(cudaGetLastError());
   h->last_launches++;
   return 0;
@@ -316,20 +421,27 @@ int sync_all(lbm_lattice* h)
   return 0;
 }
 
-// all ranks have reached this point and their streams are idle (multi-process mode only)
-int comm_barrier(lbm_lattice* h)
+// all ranks have reached this point and their streams are idle (multi-process mode only); the sum
+// of `flag` over the ranks comes back in *flag_sum, so that every rank can fail together
+int comm_barrier(lbm_lattice* h, long long flag = 0, long long* flag_sum = nullptr)
 {
+  if (flag_sum) *flag_sum = flag;
   if (!h->comm) return 0;
   Slab& s = h->slabs[0];
   NcclApi* n = nccl_api();
+  long long* d = h->comm->scratch64;
+  CK(cudaMemcpyAsync(d, &flag, sizeof flag, cudaMemcpyHostToDevice, s.stream));
   CK(cudaStreamSynchronize(s.stream));
-  NK(n->AllReduce(h->comm->scratch64, h->comm->scratch64, 1, ncclInt64, ncclSum, h->comm->nccl, s.stream));
+  NK(n->AllReduce(d, d, 1, ncclInt64, ncclSum, h->comm->nccl, s.stream));
+  long long out = 0;
+  CK(cudaMemcpyAsync(&out, d, sizeof out, cudaMemcpyDeviceToHost, s.stream));
   CK(cudaStreamSynchronize(s.stream));
+  if (flag_sum) *flag_sum = out;
   return 0;
 }
 
-// NCCL flavour of the halo: my first row's 4,7,8 go down, my last row's 2,5,6 go up, straight
-// from / into the plane rows of buffer `b` (each a contiguous run of nx floats)
+// NCCL flavour of the halo (one-step kernel only): my first row's 4,7,8 go down, my last row's
+// 2,5,6 go up, straight from / into the plane rows of buffer `b` (each a contiguous run of nx floats)
 int nccl_halo_exchange(lbm_lattice* h, Slab& s, int b)
 {
   NcclApi* n = nccl_api();
@@ -337,37 +449,18 @@ int nccl_halo_exchange(lbm_lattice* h, Slab& s, int b)
   const int nx = h->p.nx;
   const int lo = (c->rank + c->world - 1) % c->world, hi = (c->rank + 1) % c->world;
   float* base = s.buf[b];
-  NK(n->GroupStart());
-  for (int i = 0; i < 3; i++) {
-    NK(n->Send(base + LO_PLANES[i] * s.ps + (long long)nx, nx, ncclFloat, lo, c->nccl, s.stream));
-    NK(n->Send(base + HI_PLANES[i] * s.ps + (long long)s.rows * nx, nx, ncclFloat, hi, c->nccl, s.stream));
-    NK(n->Recv(base + LO_PLANES[i] * s.ps + (long long)(s.rows + 1) * nx, nx, ncclFloat, hi, c->nccl, s.stream));
-    NK(n->Recv(base + HI_PLANES[i] * s.ps, nx, ncclFloat, lo, c->nccl, s.stream));
+  const long long first = (long long)G * nx, last = (long long)(G + s.rows - 1) * nx;
+  ncclResult_t r = n->GroupStart();
+  for (int i = 0; i < 3 && r == ncclSuccess; i++) {
+    r = n->Send(base + LO_PLANES[i] * s.ps + first, nx, ncclFloat, lo, c->nccl, s.stream);
+    if (r == ncclSuccess) r = n->Send(base + HI_PLANES[i] * s.ps + last, nx, ncclFloat, hi, c->nccl, s.stream);
+    if (r == ncclSuccess) r = n->Recv(base + LO_PLANES[i] * s.ps + last + nx, nx, ncclFloat, hi, c->nccl, s.stream);
+    if (r == ncclSuccess) r = n->Recv(base + HI_PLANES[i] * s.ps + first - nx, nx, ncclFloat, lo, c->nccl, s.stream);
   }
-  NK(n->GroupEnd());
+  const ncclResult_t e = n->GroupEnd();     // always paired with GroupStart
+  if (r == ncclSuccess) r = e;
+  if (r != ncclSuccess) return fail("NCCL error during the halo exchange: %s", n->GetErrorString(r));
   return 0;
-}
-
-// after the resident state changed from outside (upload / init): fill every ghost row
-int refresh_ghosts(lbm_lattice* h)
-{
-  if (sync_all(h)) return 1;
-  if (comm_barrier(h)) return 1;
-  const int nx = h->p.nx;
-  for (auto& s : h->slabs) {
-    CK(cudaSetDevice(s.device));
-    if (h->comm && h->comm->halo == HALO_NCCL) {
-      if (nccl_halo_exchange(h, s, h->cur)) return 1;
-      continue;
-    }
-    const int c = h->cur;
-    lbm::halo_push_kernel<<<(nx + 255) / 256, 256, 0, s.stream>>>(
-        s.buf[c], s.ps, nx, s.rows, s.ghost_lo[c][0], s.ghost_lo[c][1], s.ghost_lo[c][2],
-        s.ghost_hi[c][0], s.ghost_hi[c][1], s.ghost_hi[c][2]);
-    CK(cudaGetLastError());
-  }
-  if (sync_all(h)) return 1;
-  return comm_barrier(h);
 }
 
 int ensure_totals(lbm_lattice* h, long long iters)
@@ -391,11 +484,11 @@ int build_graph(lbm_lattice* h, Slab& s, int cur)
   CK(cudaStreamBeginCapture(s.stream, cudaStreamCaptureModeThreadLocal));
   int c = cur;
   for (int i = 0; i < h->chunk; i++) {
-    const StepArgs a = make_args(h, s, c, 1, i);
+    const StepArgs a = make_args(h, s, c, 1, i, 0);
     CK(launch_step(h->vec, h->tpb, a, s.nblk, s.stream, h->use_pdl && i > 0));
     c ^= 1;
   }
-  lbm::reduce_partials_kernel<<<h->chunk, 256, 0, s.stream>>>(s.partials, s.np, s.nblk, s.nblk, s.totals, s.counter);
+  lbm::reduce_partials_kernel<<<h->chunk, 256, 0, s.stream>>>(s.partials, s.np, s.nblk, s.totals, s.counter);
   CK(cudaGetLastError());
   lbm::advance_counter_kernel<<<1, 1, 0, s.stream>>>(s.counter, h->chunk);
   CK(cudaGetLastError());
@@ -411,48 +504,63 @@ void drop_graphs(Slab& s)
     if (s.graph[i]) { cudaGraphExecDestroy(s.graph[i]); s.graph[i] = nullptr; }
 }
 
-// ---- two-step passes (LBM_FUSE=2) ---------------------------------------------------------------
-// Two-step passes halve the DRAM traffic but cost ~20 % more instructions and run at lower
-// occupancy: they win once a slab streams from HBM (+17 % at 16384^2, profiles/r1_tuning.md) and lose
-// when it lives in L2 (1024^2: -40 %), so "auto" turns them on from 8 M cells (0.6 GB of state) up.
-bool fused_ok(const lbm_lattice* h)
+// ---- S timesteps per pass (the streaming kernel) -------------------------------------------------
+// Fewer bytes per update (72 / S + halo) at the price of lower occupancy and ~7 % redundant columns:
+// wins once a slab streams from HBM and loses when it lives in L2, so "auto" turns it on from
+// 8 M cells (0.6 GB of state) per slab up.
+int stream_steps(const lbm_lattice* h)
 {
   // decided from global quantities only: every rank of a ring must take the same path
   const int min_rows = h->p.ny / h->world;
-  if (h->fuse_mode == 1 || h->slabs.size() != 1 || h->vec != 4 || h->p.nx < 128 || min_rows < 4) return false;
-  if (h->comm && (h->comm->halo != HALO_P2P || h->comm->per_step_allreduce)) return false;
-  if (h->fuse_mode == 2) return true;
-  return (long long)min_rows * h->p.nx >= (8LL << 20);
+  const int nx = h->p.nx;
+  if (h->fuse_mode == 1 || nx % 16 != 0 || nx < 128 || min_rows < 4 * G) return 1;
+  if (h->comm && h->comm->halo != HALO_P2P) return 1;
+  if (!encode_tiled_fn()) return 1;
+  const int s = STREAM_CFGS[h->stream_cfg].s;
+  if (h->fuse_mode >= 2) return s;
+  return ((long long)min_rows * nx >= (8LL << 20)) ? s : 1;
 }
 
-// t -> t+2 on rows 2..rows-1 of buffer cur^1, t+1 boundary rows into the strips (slots: 2 steps)
-// tile shapes of the two-step kernel: {threads, rows relaxed to t+1, min blocks per SM}
-struct FusedCfg { int tpb, ra, minb; };
-// {224,14,3} measured best on B200 (profiles/r1_tuning.md section 7): 7 warps x 2 rows, 64.5 KB of shared
-// memory, 80 registers, 3 blocks per SM (193 KB of shared memory in use leaves the L1 some room)
-const FusedCfg FUSED_CFGS[] = {{224, 14, 3}, {256, 16, 2}, {288, 18, 2}, {320, 20, 2}, {192, 12, 3}, {160, 10, 4}};
-int g_fused_cfg = 0;
-
-template <int TPB, int RA, int MINB>
-int launch_fused_t(const lbm::FusedArgs& a, int ntiles, cudaStream_t st)
+template <int S, int NW, int K0, int MINB>
+int launch_stream_t(const CUtensorMap& ts, const CUtensorMap& tf, const StreamArgs& a, const lbm::StepReduce& r,
+                    int ntiles, cudaStream_t st)
 {
-  // the opt-in to > 48 KB of dynamic shared memory is a per-device function attribute
-  static bool configured[64] = {};
-  int dev = 0;
-  CK(cudaGetDevice(&dev));
-  if (dev >= 0 && dev < 64 && !configured[dev]) {
-    CK(cudaFuncSetAttribute(lbm::lbm_fused2_kernel<TPB, RA, MINB>,
-                            cudaFuncAttributeMaxDynamicSharedMemorySize, lbm::fused_smem(RA)));
-    configured[dev] = true;
-  }
-  lbm::lbm_fused2_kernel<TPB, RA, MINB><<<ntiles, TPB, lbm::fused_smem(RA), st>>>(a);
+  constexpr int SMEM = lbm::stream_smem_bytes(S, NW, K0);
+  lbm::lbm_stream_kernel<S, NW, K0, MINB><<<ntiles, (S * NW + 1) * 32, SMEM, st>>>(ts, tf, a, r);
   CK(cudaGetLastError());
   return 0;
 }
 
-int launch_fused(lbm_lattice* h, Slab& s, int cur, int fuse_b, int slot)
+template <int S, int NW, int K0, int MINB>
+cudaError_t configure_stream_t()
 {
-  lbm::FusedArgs a{};
+  return cudaFuncSetAttribute(lbm::lbm_stream_kernel<S, NW, K0, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              lbm::stream_smem_bytes(S, NW, K0));
+}
+
+#define LBM_STREAM_DISPATCH(idx, CALL)                 \
+  switch (idx) {                                       \
+    case 1: return CALL(3, 6, 3, 1);                   \
+    case 2: return CALL(2, 8, 3, 1);                   \
+    case 3: return CALL(4, 4, 2, 1);                   \
+    case 4: return CALL(2, 3, 2, 3);                   \
+    case 5: return CALL(1, 4, 4, 3);                   \
+    case 6: return CALL(3, 4, 2, 1);                   \
+    default: return CALL(2, 4, 3, 2);                  \
+  }
+
+// the opt-in to > 48 KB of dynamic shared memory is a per-device function attribute
+cudaError_t configure_stream(int cfg)
+{
+#define LBM_CALL(S, NW, K0, MINB) configure_stream_t<S, NW, K0, MINB>()
+  LBM_STREAM_DISPATCH(cfg, LBM_CALL)
+#undef LBM_CALL
+}
+
+// t -> t+S on every owned row of buffer cur^1 (+ the neighbours' ghost zones); slots: S steps
+int launch_stream(lbm_lattice* h, Slab& s, int cur, int fuse_last, int slot, long long step_index)
+{
+  StreamArgs a{};
   a.src = s.buf[cur];
   a.dst = s.buf[cur ^ 1];
   a.flags = s.flags;
@@ -461,58 +569,137 @@ int launch_fused(lbm_lattice* h, Slab& s, int cur, int fuse_b, int slot)
   a.rows = s.rows;
   a.tiles_x = s.tiles_x;
   a.tiles_y = s.tiles_y;
+  a.tile_h = s.tile_h;
+  a.src_plane0 = 9 * cur;
   a.omega = h->p.omega;
   a.a1 = h->a1;
   a.a2 = h->a2;
-  a.fuse_b = fuse_b;
-  a.strip_lo = s.strip_lo;
-  a.strip_hi = s.strip_hi;
-  a.pse = s.pse;
-  for (int i = 0; i < 3; i++) { a.nb_lo[i] = s.nb_lo[i]; a.nb_hi[i] = s.nb_hi[i]; }
-  a.partials_a = s.partials + (long long)slot * s.np;
-  a.partials_b = s.partials + (long long)(slot + 1) * s.np;
-  if (h->comm && h->comm->in_kernel) {
-    const Comm* c = h->comm;
+  a.fuse_last = fuse_last;
+  a.ghost_lo = s.gz_lo[cur ^ 1];
+  a.ghost_hi = s.gz_hi[cur ^ 1];
+  a.ps_lo = s.lo_ps;
+  a.ps_hi = s.hi_ps;
+  a.partials = s.partials + (long long)slot * s.np;
+  a.np = s.np;
+  if (h->ring) {
     a.ring_in = s.sync;
-    a.ring_out_lo = c->peer_lo_flag;
-    a.ring_out_hi = c->peer_hi_flag;
+    a.ring_out_lo = h->stall_test ? s.sync + 8 : s.ring_out_lo;
+    a.ring_out_hi = h->stall_test ? s.sync + 8 : s.ring_out_hi;
     a.ring_tickets = s.sync + 4;
     a.ring_timeout = s.sync + 2;
-    a.ring_step = c->steps_done;
-    a.rot = s.tiles_x;
+    a.ring_phase = h->phase;
   }
+  lbm::StepReduce r;
+  fill_reduce(h, s, r, step_index);
   const int nt = s.tiles_x * s.tiles_y;
-  switch (g_fused_cfg) {
-    case 1: return launch_fused_t<256, 16, 2>(a, nt, s.stream);
-    case 2: return launch_fused_t<288, 18, 2>(a, nt, s.stream);
-    case 3: return launch_fused_t<320, 20, 2>(a, nt, s.stream);
-    case 4: return launch_fused_t<192, 12, 3>(a, nt, s.stream);
-    case 5: return launch_fused_t<160, 10, 4>(a, nt, s.stream);
-    default: return launch_fused_t<224, 14, 3>(a, nt, s.stream);
-  }
+#define LBM_CALL(S, NW, K0, MINB) launch_stream_t<S, NW, K0, MINB>(s.tm_state, s.tm_flags, a, r, nt, s.stream)
+  LBM_STREAM_DISPATCH(h->stream_cfg, LBM_CALL)
+#undef LBM_CALL
 }
 
-// rows 1 and `rows` of time t+2 from the strips (which now hold the neighbours' t+1 rows too):
-// two launches of the ordinary step kernel on 3-row mini slabs; they also push the t+2 ghost rows
-int launch_fixups(lbm_lattice* h, Slab& s, int cur, int fuse_b, int slot)
+// one-step launches of one timestep on every slab (+ the ordering / halo launches of the slow variants)
+int launch_one_step(lbm_lattice* h, int cur, int fuse, int slot, long long step_index, bool pdl)
 {
-  const int nx = h->p.nx, nxv = nx / h->vec;
-  const int nb_strip = (nxv + h->tpb - 1) / h->tpb;
-  const int ntiles = s.tiles_x * s.tiles_y;
-  for (int hi = 0; hi < 2; hi++) {
-    StepArgs a = make_args(h, s, cur, fuse_b, slot);
-    a.src = hi ? s.strip_hi : s.strip_lo;
-    a.ps = s.pse;
-    a.ps_dst = s.ps;
-    a.rows = 1;
-    a.nvec = nxv;
-    a.dst_delta = hi ? (long long)(s.rows - 1) * nx : 0;
-    a.push = hi ? 2 : 1;
-    a.partials = s.partials + (long long)slot * s.np + ntiles + hi * nb_strip;
-    a.rot = 0;                // ring ordering (if done in the kernel): this strip's side only, see `push`
-    a.nb_lo = a.nb_hi = nb_strip;
-    CK(launch_step(h->vec, h->tpb, a, nb_strip, s.stream));
+  Comm* comm = h->comm;
+  const bool launches_order = h->ring && !h->ring_in_kernel;
+  for (auto& s : h->slabs) {
+    CK(cudaSetDevice(s.device));
+    // my ring neighbours must have finished the previous phase: their stores into my ghost rows are
+    // complete and they no longer read the ghost rows I am about to overwrite
+    if (launches_order) {
+      lbm::wait_neighbours_kernel<<<1, 2, 0, s.stream>>>(s.sync, h->phase, s.sync + 2);
+      CK(cudaGetLastError());
+      h->last_launches++;
+    }
+    const StepArgs a = make_args(h, s, cur, fuse, slot, step_index);
+    CK(launch_step(h->vec, h->tpb, a, s.nblk, s.stream, pdl));
+    h->last_launches++;
+    if (launches_order) {
+      lbm::signal_neighbours_kernel<<<1, 2, 0, s.stream>>>(h->stall_test ? s.sync + 8 : s.ring_out_lo,
+                                                           h->stall_test ? s.sync + 8 : s.ring_out_hi, h->phase + 1);
+      CK(cudaGetLastError());
+      h->last_launches++;
+    } else if (comm && comm->halo == HALO_NCCL) {
+      if (nccl_halo_exchange(h, s, cur ^ 1)) return 1;
+      h->last_launches++;
+    }
   }
+  h->phase++;
+  return 0;
+}
+
+// second stage of the reduction for the `nsteps` steps just launched; their partials are per tile
+// (streaming passes) or per block (one-step launches)
+int reduce_chunk(lbm_lattice* h, int nsteps, bool tiles)
+{
+  if (h->reduce_per_step) return 0;     // done by the last block of every launch
+  for (auto& s : h->slabs) {
+    CK(cudaSetDevice(s.device));
+    lbm::reduce_partials_kernel<<<nsteps, 256, 0, s.stream>>>(s.partials, s.np,
+                                                             tiles ? s.tiles_x * s.tiles_y : s.nblk,
+                                                             s.totals, s.counter);
+    CK(cudaGetLastError());
+    lbm::advance_counter_kernel<<<1, 1, 0, s.stream>>>(s.counter, nsteps);
+    CK(cudaGetLastError());
+  }
+  h->last_launches += 2 * (long long)h->slabs.size();
+  return 0;
+}
+
+// the time loop proper: `iters` timesteps starting at absolute step index `step0` of this run
+int run_steps(lbm_lattice* h, int iters, long long step0, bool last_segment)
+{
+  const size_t nslab = h->slabs.size();
+  int remaining = iters;
+  int cur = h->cur;
+  long long step = step0;
+  // steps still to come after this segment keep the pre-acceleration going
+  const int more = last_segment ? 0 : 1;
+
+  const int S = stream_steps(h);
+  if (S > 1) {
+    while (remaining >= S) {
+      const int passes = std::min(remaining / S, std::max(1, h->chunk / S));
+      for (int j = 0; j < passes; j++) {
+        const int fuse_last = (remaining - S * (j + 1) + more) > 0;
+        for (auto& s : h->slabs) {
+          CK(cudaSetDevice(s.device));
+          if (launch_stream(h, s, cur, fuse_last, S * j, step)) return 1;
+        }
+        h->phase++;
+        h->last_launches += (long long)nslab;
+        step += S;
+        cur ^= 1;
+      }
+      if (reduce_chunk(h, S * passes, true)) return 1;
+      remaining -= S * passes;
+    }
+  }
+
+  if (nslab == 1 && h->world == 1 && h->use_graph) {
+    Slab& s = h->slabs[0];
+    while (remaining > h->chunk) {
+      if (!s.graph[cur] && build_graph(h, s, cur)) return 1;
+      CK(cudaGraphLaunch(s.graph[cur], s.stream));
+      h->last_launches += h->chunk + 2;
+      remaining -= h->chunk;                    // chunk is even: parity unchanged
+      step += h->chunk;
+    }
+  }
+
+  // remaining steps as plain launches, reduced chunk by chunk; the very last step of the run
+  // leaves the state un-accelerated
+  while (remaining > 0) {
+    const int n = std::min(remaining, h->chunk);
+    for (int i = 0; i < n; i++, step++) {
+      const int fuse = (remaining - i - 1 + more) > 0;
+      if (launch_one_step(h, cur, fuse, i, step, h->use_pdl && h->world == 1 && i > 0)) return 1;
+      cur ^= 1;
+    }
+    if (reduce_chunk(h, n, false)) return 1;
+    remaining -= n;
+  }
+  h->cur = cur;
   return 0;
 }
 
@@ -522,7 +709,7 @@ int run_impl(lbm_lattice* h, int iters, double* av_out)
   h->last_launches = 0;
   if (iters < 0) return fail("lbm_run: negative iteration count");
   if (iters == 0) return 0;
-  const size_t nslab = h->slabs.size();
+  if (h->poisoned) return fail("lbm_run: an earlier run on this handle failed half-way; create a new one");
   Comm* comm = h->comm;
   const long long totals_before = h->slabs[0].totals_cap;
   if (ensure_totals(h, iters)) return 1;
@@ -536,145 +723,43 @@ int run_impl(lbm_lattice* h, int iters, double* av_out)
     CK(cudaMemsetAsync(s.counter, 0, sizeof(long long), s.stream));
     CK(cudaEventRecord(s.ev_begin, s.stream));
     if (launch_accelerate(h, s, h->cur)) return 1;
-  }
-
-  int remaining = iters;
-  int cur = h->cur;
-  // ---- two timesteps per pass while at least two remain (LBM_FUSE=2)
-  if (fused_ok(h)) {
-    Slab& s = h->slabs[0];
-    const int ntiles = s.tiles_x * s.tiles_y;
-    const int nb_strip = ((h->p.nx / h->vec) + h->tpb - 1) / h->tpb;
-    while (remaining >= 2) {
-      const int pairs = std::min(remaining / 2, h->chunk / 2);
-      for (int j = 0; j < pairs; j++) {
-        const int fuse_b = (remaining - 2 * j - 2) > 0;
-        const bool launches_order = comm && !comm->in_kernel;   // else the kernels order themselves
-        if (launches_order) {
-          lbm::wait_neighbours_kernel<<<1, 2, 0, s.stream>>>(s.sync, comm->steps_done, s.sync + 2);
-          CK(cudaGetLastError());
-        }
-        if (launch_fused(h, s, cur, fuse_b, 2 * j)) return 1;
-        if (launches_order) {   // my t+1 boundary rows are in the neighbours' strips; wait for theirs
-          lbm::signal_neighbours_kernel<<<1, 2, 0, s.stream>>>(comm->peer_lo_flag, comm->peer_hi_flag,
-                                                               comm->steps_done + 1);
-          CK(cudaGetLastError());
-          lbm::wait_neighbours_kernel<<<1, 2, 0, s.stream>>>(s.sync, comm->steps_done + 1, s.sync + 2);
-          CK(cudaGetLastError());
-        }
-        if (comm) comm->steps_done++;
-        if (launch_fixups(h, s, cur, fuse_b, 2 * j + 1)) return 1;
-        if (launches_order) {
-          lbm::signal_neighbours_kernel<<<1, 2, 0, s.stream>>>(comm->peer_lo_flag, comm->peer_hi_flag,
-                                                               comm->steps_done + 1);
-          CK(cudaGetLastError());
-        }
-        if (comm) comm->steps_done++;
-        h->last_launches += launches_order ? 7 : 3;
-        cur ^= 1;
-      }
-      lbm::reduce_partials_kernel<<<2 * pairs, 256, 0, s.stream>>>(s.partials, s.np, ntiles,
-                                                                   ntiles + 2 * nb_strip, s.totals, s.counter);
-      CK(cudaGetLastError());
-      lbm::advance_counter_kernel<<<1, 1, 0, s.stream>>>(s.counter, 2 * pairs);
-      CK(cudaGetLastError());
-      h->last_launches += 2;
-      remaining -= 2 * pairs;
+    if (comm && comm->halo == HALO_NCCL) {
+      if (nccl_halo_exchange(h, s, h->cur)) return 1;
+    } else if (launch_refresh(h, s, h->cur)) {
+      return 1;
     }
   }
+  if (h->ring) h->phase++;
 
-  if (nslab == 1 && !comm && h->use_graph) {
-    Slab& s = h->slabs[0];
-    while (remaining > h->chunk) {
-      if (!s.graph[cur] && build_graph(h, s, cur)) return 1;
-      CK(cudaGraphLaunch(s.graph[cur], s.stream));
-      h->last_launches += h->chunk + 2;
-      remaining -= h->chunk;                    // chunk is even: parity unchanged
+  std::fill(av_out, av_out + iters, 0.0);
+  std::vector<double> tmp;
+  int rc = 0;
+  if (!h->reduce_per_step) {
+    rc = run_steps(h, iters, 0, true);
+  } else {
+    // LBM_REDUCE=step: every launch pushes its steps' slab totals to all ranks; the arrays hold
+    // ALLRED_CAP steps, so longer runs are drained segment by segment
+    tmp.resize((size_t)ALLRED_CAP * h->world);
+    for (long long done = 0; done < iters && rc == 0;) {
+      const int seg = (int)std::min<long long>(iters - done, ALLRED_CAP);
+      rc = run_steps(h, seg, done, done + seg == iters);
+      if (rc) break;
+      if (sync_all(h) || comm_barrier(h)) { rc = 1; break; }      // everybody's pushes have landed
+      Slab& s = h->slabs[0];      // every slab holds the same numbers
+      CK(cudaSetDevice(s.device));
+      CK(cudaMemcpy(tmp.data(), s.allred, sizeof(double) * tmp.size(), cudaMemcpyDeviceToHost));
+      for (int r = 0; r < h->world; r++)       // fixed rank order: deterministic, identical everywhere
+        for (int t = 0; t < seg; t++) av_out[done + t] += tmp[(size_t)r * ALLRED_CAP + (done + t) % ALLRED_CAP];
+      done += seg;
     }
   }
+  if (rc) { h->poisoned = h->ring; return 1; }
 
-  // remaining steps as plain launches, reduced chunk by chunk; the very last step of the run
-  // leaves the state un-accelerated
-  long long step_no = 0;     // steps launched one by one in this run (graph chunks never coexist with them)
-  if (comm && comm->per_step_allreduce && comm->step_sums_cap < iters) {
-    if (comm->step_sums) CK(cudaFree(comm->step_sums));
-    comm->step_sums = nullptr;
-    CK(cudaMalloc(&comm->step_sums, sizeof(double) * h->slabs[0].totals_cap));
-    comm->step_sums_cap = h->slabs[0].totals_cap;
-  }
-  while (remaining > 0) {
-    const int n = std::min(remaining, h->chunk);
-    for (int i = 0; i < n; i++, step_no++) {
-      const int fuse = (remaining - i) > 1;
-      for (size_t k = 0; k < nslab; k++) {
-        Slab& s = h->slabs[k];
-        CK(cudaSetDevice(s.device));
-        // my ring neighbours must have finished the previous step: their stores into my ghost
-        // rows are complete and they no longer read the ghost rows I am about to overwrite
-        if (nslab > 1 && step_no > 0) {
-          const Slab& lo = h->slabs[(k + nslab - 1) % nslab];
-          const Slab& hi = h->slabs[(k + 1) % nslab];
-          CK(cudaStreamWaitEvent(s.stream, lo.ev_step[(step_no - 1) & 1], 0));
-          CK(cudaStreamWaitEvent(s.stream, hi.ev_step[(step_no - 1) & 1], 0));
-        }
-        if (comm && comm->halo == HALO_P2P && !comm->in_kernel) {
-          lbm::wait_neighbours_kernel<<<1, 2, 0, s.stream>>>(s.sync, comm->steps_done, s.sync + 2);
-          CK(cudaGetLastError());
-          h->last_launches++;
-        }
-        const StepArgs a = make_args(h, s, cur, fuse, i);
-        CK(launch_step(h->vec, h->tpb, a, s.nblk, s.stream, h->use_pdl && nslab == 1 && !comm && i > 0));
-        if (nslab > 1) CK(cudaEventRecord(s.ev_step[step_no & 1], s.stream));
-        if (comm && comm->halo == HALO_P2P && !comm->in_kernel) {
-          lbm::signal_neighbours_kernel<<<1, 2, 0, s.stream>>>(comm->peer_lo_flag, comm->peer_hi_flag,
-                                                               comm->steps_done + 1);
-          CK(cudaGetLastError());
-          h->last_launches++;
-        } else if (comm && comm->halo == HALO_NCCL) {
-          if (nccl_halo_exchange(h, s, cur ^ 1)) return 1;
-          h->last_launches++;
-        }
-      }
-      if (comm && comm->per_step_allreduce) {
-        // the north-star formulation: this step's slab total -> all ranks, right away
-        Slab& s = h->slabs[0];
-        const long long idx = step_no;
-        lbm::reduce_partials_kernel<<<1, 256, 0, s.stream>>>(s.partials + (long long)i * s.np, s.np, s.nblk,
-                                                            s.nblk, s.totals + idx, comm->scratch64);
-        CK(cudaGetLastError());
-        CK(cudaEventRecord(comm->ev_side, s.stream));
-        CK(cudaStreamWaitEvent(comm->side, comm->ev_side, 0));
-        NK(nccl_api()->AllReduce(s.totals + idx, comm->step_sums + idx, 1, ncclDouble, ncclSum,
-                                 comm->nccl, comm->side));
-        h->last_launches += 2;
-      }
-      if (comm) comm->steps_done++;
-      h->last_launches += (long long)nslab;
-      cur ^= 1;
-    }
-    if (!(comm && comm->per_step_allreduce)) {
-      for (auto& s : h->slabs) {
-        CK(cudaSetDevice(s.device));
-        lbm::reduce_partials_kernel<<<n, 256, 0, s.stream>>>(s.partials, s.np, s.nblk, s.nblk, s.totals, s.counter);
-        CK(cudaGetLastError());
-        lbm::advance_counter_kernel<<<1, 1, 0, s.stream>>>(s.counter, n);
-        CK(cudaGetLastError());
-      }
-      h->last_launches += 2 * (long long)nslab;
-    }
-    remaining -= n;
-  }
-  h->cur = cur;
-
-  if (comm && comm->per_step_allreduce) {      // the run is over when its last allreduce is
-    CK(cudaEventRecord(comm->ev_side, comm->side));
-    CK(cudaStreamWaitEvent(h->slabs[0].stream, comm->ev_side, 0));
-  }
   for (auto& s : h->slabs) {
     CK(cudaSetDevice(s.device));
     CK(cudaEventRecord(s.ev_end, s.stream));
   }
-  if (sync_all(h)) return 1;
+  if (sync_all(h)) { h->poisoned = h->ring; return 1; }
   float ms_max = 0;
   for (auto& s : h->slabs) {
     float ms = 0;
@@ -684,46 +769,52 @@ int run_impl(lbm_lattice* h, int iters, double* av_out)
   }
   h->last_ms = ms_max;
 
-  if (comm) {
-    unsigned timed_out = 0;
-    CK(cudaMemcpy(&timed_out, h->slabs[0].sync + 2, sizeof timed_out, cudaMemcpyDeviceToHost));
-    if (timed_out) return fail("lbm_run: timed out waiting for a neighbour GPU (rank %d)", comm->rank);
+  // a neighbour that never showed up: every slab of the ring fails together
+  long long timed_out = 0;
+  if (h->ring) {
+    for (auto& s : h->slabs) {
+      unsigned t = 0;
+      CK(cudaSetDevice(s.device));
+      CK(cudaMemcpy(&t, s.sync + 2, sizeof t, cudaMemcpyDeviceToHost));
+      timed_out += t;
+    }
+    long long all = timed_out;
+    if (comm_barrier(h, timed_out, &all)) { h->poisoned = true; return 1; }
+    if (all) {
+      h->poisoned = true;
+      return fail("lbm_run: timed out waiting for a neighbour GPU (slab %d of %d)", h->slabs[0].rank, h->world);
+    }
   }
 
-  std::fill(av_out, av_out + iters, 0.0);
-  std::vector<double> tmp((size_t)iters);
-  if (!comm) {
-    for (auto& s : h->slabs) {          // fixed slab order: the cross-GPU sum is deterministic
-      CK(cudaSetDevice(s.device));
-      CK(cudaMemcpy(tmp.data(), s.totals, sizeof(double) * iters, cudaMemcpyDeviceToHost));
-      for (int t = 0; t < iters; t++) av_out[t] += tmp[t];
+  if (!h->reduce_per_step) {
+    tmp.resize((size_t)iters);
+    if (!comm) {
+      for (auto& s : h->slabs) {          // fixed slab order: the cross-GPU sum is deterministic
+        CK(cudaSetDevice(s.device));
+        CK(cudaMemcpy(tmp.data(), s.totals, sizeof(double) * iters, cudaMemcpyDeviceToHost));
+        for (int t = 0; t < iters; t++) av_out[t] += tmp[t];
+      }
+    } else {
+      // all-gather every rank's per-step totals, then add them in rank order on the host
+      Slab& s = h->slabs[0];
+      double* gathered = nullptr;
+      CK(cudaMalloc(&gathered, sizeof(double) * (size_t)iters * comm->world));
+      const ncclResult_t nr = nccl_api()->AllGather(s.totals, gathered, (size_t)iters, ncclDouble,
+                                                    comm->nccl, s.stream);
+      cudaError_t ce = nr == ncclSuccess ? cudaStreamSynchronize(s.stream) : cudaErrorUnknown;
+      for (int r = 0; r < comm->world && ce == cudaSuccess; r++) {
+        ce = cudaMemcpy(tmp.data(), gathered + (size_t)r * iters, sizeof(double) * iters, cudaMemcpyDeviceToHost);
+        for (int t = 0; t < iters; t++) av_out[t] += tmp[t];
+      }
+      cudaFree(gathered);
+      if (nr != ncclSuccess) return fail("NCCL error gathering av_vels: %s", nccl_api()->GetErrorString(nr));
+      if (ce != cudaSuccess) return fail("CUDA error gathering av_vels: %s", cudaGetErrorString(ce));
     }
-  } else if (comm->per_step_allreduce) {
-    Slab& s = h->slabs[0];
-    CK(cudaStreamSynchronize(comm->side));
-    CK(cudaMemcpy(av_out, comm->step_sums, sizeof(double) * iters, cudaMemcpyDeviceToHost));
-    (void)s;
-  } else {
-    // all-gather every rank's per-step totals, then add them in rank order on the host
-    Slab& s = h->slabs[0];
-    double* gathered = nullptr;
-    CK(cudaMalloc(&gathered, sizeof(double) * (size_t)iters * comm->world));
-    const ncclResult_t nr = nccl_api()->AllGather(s.totals, gathered, (size_t)iters, ncclDouble,
-                                                  comm->nccl, s.stream);
-    cudaError_t ce = nr == ncclSuccess ? cudaStreamSynchronize(s.stream) : cudaErrorUnknown;
-    for (int r = 0; r < comm->world && ce == cudaSuccess; r++) {
-      ce = cudaMemcpy(tmp.data(), gathered + (size_t)r * iters, sizeof(double) * iters, cudaMemcpyDeviceToHost);
-      for (int t = 0; t < iters; t++) av_out[t] += tmp[t];
-    }
-    cudaFree(gathered);
-    if (nr != ncclSuccess) return fail("NCCL error gathering av_vels: %s", nccl_api()->GetErrorString(nr));
-    if (ce != cudaSuccess) return fail("CUDA error gathering av_vels: %s", cudaGetErrorString(ce));
   }
   const double denom = (double)h->tot_cells;
   for (int t = 0; t < iters; t++) av_out[t] /= denom;
   return 0;
 }
-
 
 void read_tuning(lbm_lattice* h)
 {
@@ -736,19 +827,89 @@ void read_tuning(lbm_lattice* h)
   // L2-resident regime (profiles/r1_tuning.md)
   const int want_tpb = env_int("LBM_TPB", 128);
   h->tpb = (want_tpb == 64 || want_tpb == 256 || want_tpb == 512) ? want_tpb : 128;
-  h->chunk = std::max(2, env_int("LBM_CHUNK", 128)) & ~1;
+  h->chunk = std::max(12, env_int("LBM_CHUNK", 120)) / 12 * 12;     // a multiple of every S
   h->use_graph = env_int("LBM_GRAPH", 1) != 0;
   h->use_pdl = env_int("LBM_PDL", -1) != 0;   // -1 = decide per slab size (create_slab)
   h->pad = std::max(0, env_int("LBM_PLANE_PAD", 0));
   h->fuse_mode = env_int("LBM_FUSE", -1);
-  g_fused_cfg = std::min(5, std::max(0, env_int("LBM_FUSE_CFG", 0)));
+  // LBM_FUSE=S picks the default tile shape for S steps per pass; LBM_STREAM_CFG picks any shape
+  int cfg = 0;
+  if (h->fuse_mode == 3) cfg = 1;
+  if (h->fuse_mode == 4) cfg = 3;
+  cfg = env_int("LBM_STREAM_CFG", cfg);
+  h->stream_cfg = std::min(N_STREAM_CFGS - 1, std::max(0, cfg));
+  if (h->fuse_mode >= 2) h->fuse_mode = STREAM_CFGS[h->stream_cfg].s;
+  h->tile_h_max = std::max(0, env_int("LBM_TILE_H", 0));
+  h->reduce_per_step = env_is("LBM_REDUCE", "step") && h->world > 1 && h->world <= lbm::MAX_REDUCE_WORLD;
+  h->stall_test = env_int("LBM_TEST_RING_STALL", -1) >= 0;
 }
 
-// device objects of one slab; obstacles_rows points at the slab's first row
-int create_slab(lbm_lattice* h, Slab& s, const int* obstacles_rows, long long* fluid_cells)
+// tile height of the streaming kernel: as tall as allowed (the S-1 extra rows above and below a
+// tile are recomputed by its neighbours), but such that the grid is close to a whole number of
+// waves of (SMs x blocks per SM) -- every tile costs the same, so a ragged last wave is idle time
+void choose_tiles(const lbm_lattice* h, Slab& s, int min_rows)
+{
+  const StreamCfg& c = STREAM_CFGS[h->stream_cfg];
+  const int nx = h->p.nx;
+  s.tiles_x = (nx + lbm::S_OUT_W - 1) / lbm::S_OUT_W;
+  const int extra = 2 * (c.s - 1);
+  const int hmax = h->tile_h_max > 0 ? h->tile_h_max : 32 * c.nw - extra;
+  const int slots = 148 * c.minb;
+  int best_h = 0;
+  double best_cost = 0;
+  // decided from the ring's smallest slab so that every slab uses the same height
+  for (int ty = (min_rows + hmax - 1) / hmax; ty <= min_rows; ty++) {
+    int hh = (min_rows + ty - 1) / ty;
+    hh = ((hh + extra + c.nw - 1) / c.nw) * c.nw - extra;      // whole batches
+    if (hh < 1) hh = c.nw > extra ? c.nw - extra : c.nw;
+    if (hh > hmax && best_h) break;
+    const int tiles = s.tiles_x * ((min_rows + hh - 1) / hh);
+    const int waves = (tiles + slots - 1) / slots;
+    const double cost = (double)waves * (hh + extra + 6);       // + per-tile prologue, in row units
+    if (!best_h || cost < best_cost) { best_h = hh; best_cost = cost; }
+    if (hh * 3 < hmax) break;                                  // not below a third of the maximum
+  }
+  s.tile_h = std::max(best_h, 1);
+  s.tiles_y = (s.rows + s.tile_h - 1) / s.tile_h;
+}
+
+int make_tensor_maps(const lbm_lattice* h, Slab& s)
+{
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return fail("cuTensorMapEncodeTiled is not available from this driver");
+  const StreamCfg& c = STREAM_CFGS[h->stream_cfg];
+  const cuuint64_t nx = (cuuint64_t)h->p.nx, nrows = (cuuint64_t)(s.rows + 2 * G);
+  {
+    const cuuint64_t dims[3] = {nx, nrows, 18};
+    const cuuint64_t strides[2] = {nx * 4, (cuuint64_t)s.ps * 4};
+    const cuuint32_t box[3] = {(cuuint32_t)lbm::S_TILE_W, (cuuint32_t)c.nw, 1};
+    const cuuint32_t es[3] = {1, 1, 1};
+    const CUresult r = enc(&s.tm_state, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, s.base, dims, strides, box, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled (populations) failed with CUresult %d", (int)r);
+  }
+  {
+    const cuuint64_t dims[2] = {nx, nrows};
+    const cuuint64_t strides[1] = {nx};
+    const cuuint32_t box[2] = {(cuuint32_t)lbm::S_TILE_W, (cuuint32_t)c.nw};
+    const cuuint32_t es[2] = {1, 1};
+    const CUresult r = enc(&s.tm_flags, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, s.flags, dims, strides, box, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled (flags) failed with CUresult %d", (int)r);
+  }
+  return 0;
+}
+
+// device objects of one slab.  obstacles: `rows_given` rows starting at lattice row `row_first`
+// (the whole grid in one-process mode, the slab's own rows in rank mode); flag rows whose lattice
+// row is not among them (ghost rows in rank mode) are left for the neighbours to push.
+int create_slab(lbm_lattice* h, Slab& s, const int* obstacles, int row_first, int rows_given,
+                long long* fluid_cells)
 {
   const int nx = h->p.nx, ny = h->p.ny;
-  const long long cells = (long long)(s.rows + 2) * nx;
+  const long long cells = (long long)(s.rows + 2 * G) * nx;
   s.ps = plane_stride(s.rows, nx, h->pad);
   s.nvec = (long long)s.rows * (nx / h->vec);
   if (s.nvec >= (1LL << 31)) return fail("lbm_create: slab too large for 32-bit work index");
@@ -757,7 +918,7 @@ int create_slab(lbm_lattice* h, Slab& s, const int* obstacles_rows, long long* f
   // 128^2 but -50 % at 256^2 inside graphs (profiles/r1_tuning.md), so auto = multi-wave grids only
   if (env_int("LBM_PDL", -1) < 0) h->use_pdl = s.nblk >= 148 * 8;
   s.owns_accel_row = (ny - 2 >= s.y0 && ny - 2 < s.y0 + s.rows);
-  s.accel_row = ny - 2 - s.y0 + 1;
+  s.accel_row = ny - 2 - s.y0 + G;
 
   CK(cudaSetDevice(s.device));
   cudaDeviceProp prop;
@@ -768,45 +929,47 @@ int create_slab(lbm_lattice* h, Slab& s, const int* obstacles_rows, long long* f
   CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
   CK(cudaEventCreate(&s.ev_begin));
   CK(cudaEventCreate(&s.ev_end));
-  CK(cudaEventCreateWithFlags(&s.ev_step[0], cudaEventDisableTiming));
-  CK(cudaEventCreateWithFlags(&s.ev_step[1], cudaEventDisableTiming));
-  CK(cudaMalloc(&s.base, slab_bytes(s.ps, nx)));
-  CK(cudaMemset(s.base, 0, slab_bytes(s.ps, nx)));
-  s.buf[0] = reinterpret_cast<float*>(s.base);
-  s.buf[1] = s.buf[0] + 9 * s.ps;
-  s.sync = reinterpret_cast<unsigned*>(s.buf[1] + 9 * s.ps);
-  s.pse = strip_stride(nx);
-  s.strip_lo = strip_of(s.base, s.ps, nx, 0);
-  s.strip_hi = strip_of(s.base, s.ps, nx, 1);
-  s.tiles_x = (nx + lbm::F_TX - 1) / lbm::F_TX;
-  {
-    const int ty = FUSED_CFGS[g_fused_cfg].ra - 2;
-    s.tiles_y = (std::max(s.rows - 2, 0) + ty - 1) / ty;
+  const size_t bytes = slab_bytes_total(s.ps, s.rows, nx, h->world);
+  CK(cudaMalloc(&s.base, bytes));
+  CK(cudaMemsetAsync(s.base, 0, bytes, s.stream));
+  s.buf[0] = buf_of(s.base, s.ps, 0);
+  s.buf[1] = buf_of(s.base, s.ps, 1);
+  s.sync = sync_of(s.base, s.ps);
+  s.flags = flags_of(s.base, s.ps);
+  s.allred = allred_of(s.base, s.ps, s.rows, nx);
+  const int min_rows = ny / h->world;
+  if (stream_steps(h) > 1) {
+    choose_tiles(h, s, min_rows);
+    if (make_tensor_maps(h, s)) return 1;
+    const cudaError_t e = configure_stream(h->stream_cfg);
+    if (e != cudaSuccess) return fail("cudaFuncSetAttribute(shared memory): %s", cudaGetErrorString(e));
   }
-  {
-    const int nb_strip = ((nx / h->vec) + h->tpb - 1) / h->tpb;
-    s.np = std::max(s.nblk, s.tiles_x * s.tiles_y + 2 * nb_strip);
-  }
-  CK(cudaMalloc(&s.flags, (size_t)cells));
+  s.np = std::max(s.nblk, s.tiles_x * s.tiles_y);
   CK(cudaMalloc(&s.partials, sizeof(double) * (size_t)h->chunk * s.np));
   CK(cudaMalloc(&s.counter, sizeof(long long)));
-  CK(cudaMemset(s.counter, 0, sizeof(long long)));
+  CK(cudaMemsetAsync(s.counter, 0, sizeof(long long), s.stream));
 
-  // flags: bit 0 obstacle, bit 1 fluid cell of the accelerated row (global ny-2)
+  // flags: bit 0 obstacle, bit 1 fluid cell of the accelerated row (global ny-2); ghost rows carry
+  // the flags of the lattice rows they mirror (periodic in y)
   std::vector<uint8_t> fl((size_t)cells, 0);
   long long fluid = 0;
-  for (int r = 0; r < s.rows; r++) {
-    const int gy = s.y0 + r;
-    const int* orow = obstacles_rows + (size_t)r * nx;
-    uint8_t* frow = fl.data() + (size_t)(r + 1) * nx;
+#pragma omp parallel for reduction(+ : fluid) schedule(static)
+  for (int r = 0; r < s.rows + 2 * G; r++) {
+    const int gy = ((s.y0 + r - G) % ny + ny) % ny;
+    int src = gy - row_first;
+    if (src < 0 || src >= rows_given) continue;
+    const bool owned = r >= G && r < G + s.rows;
+    const int* orow = obstacles + (size_t)src * nx;
+    uint8_t* frow = fl.data() + (size_t)r * nx;
     for (int x = 0; x < nx; x++) {
       const bool ob = orow[x] != 0;
       frow[x] = (uint8_t)((ob ? lbm::FLAG_OBSTACLE : 0) | ((!ob && gy == ny - 2) ? lbm::FLAG_ACCEL : 0));
-      fluid += !ob;
+      if (owned) fluid += !ob;
     }
   }
   *fluid_cells += fluid;
-  CK(cudaMemcpy(s.flags, fl.data(), (size_t)cells, cudaMemcpyHostToDevice));
+  CK(cudaMemcpyAsync(s.flags, fl.data(), (size_t)cells, cudaMemcpyHostToDevice, s.stream));
+  CK(cudaStreamSynchronize(s.stream));
   return 0;
 }
 
@@ -815,33 +978,48 @@ int create_slab(lbm_lattice* h, Slab& s, const int* obstacles_rows, long long* f
 void wire_ghosts(Slab& s, int nx, char* lo_base, int lo_rows, long long lo_ps, char* hi_base,
                  long long hi_ps)
 {
+  s.lo_base = lo_base;
+  s.hi_base = hi_base;
+  s.lo_rows = lo_rows;
+  s.lo_ps = lo_ps;
+  s.hi_ps = hi_ps;
   for (int b = 0; b < 2; b++) {
-    float* lo_buf = reinterpret_cast<float*>(lo_base) + (long long)b * 9 * lo_ps;
-    float* hi_buf = reinterpret_cast<float*>(hi_base) + (long long)b * 9 * hi_ps;
+    float* lo_buf = buf_of(lo_base, lo_ps, b);
+    float* hi_buf = buf_of(hi_base, hi_ps, b);
+    s.gz_lo[b] = lo_buf + (long long)(G + lo_rows) * nx;
+    s.gz_hi[b] = hi_buf;
     for (int i = 0; i < 3; i++) {
-      s.ghost_lo[b][i] = lo_buf + LO_PLANES[i] * lo_ps + (long long)(lo_rows + 1) * nx;
-      s.ghost_hi[b][i] = hi_buf + HI_PLANES[i] * hi_ps;
+      s.ghost_lo[b][i] = lo_buf + LO_PLANES[i] * lo_ps + (long long)(G + lo_rows) * nx;
+      s.ghost_hi[b][i] = hi_buf + HI_PLANES[i] * hi_ps + (long long)(G - 1) * nx;
     }
   }
-  const long long pse = strip_stride(nx);
-  for (int i = 0; i < 3; i++) {
-    s.nb_lo[i] = strip_of(lo_base, lo_ps, nx, 1) + LO_PLANES[i] * pse + 2LL * nx;
-    s.nb_hi[i] = strip_of(hi_base, hi_ps, nx, 0) + HI_PLANES[i] * pse;
-  }
+  // my lower neighbour counts me as its UPPER neighbour (its sync[1]); the upper one as its LOWER
+  s.ring_out_lo = sync_of(lo_base, lo_ps) + 1;
+  s.ring_out_hi = sync_of(hi_base, hi_ps) + 0;
 }
 
 void set_config_string(lbm_lattice* h)
 {
-  char cfg[320];
-  const char* red = (h->comm && h->comm->per_step_allreduce) ? " reduce=allreduce-per-step" : "";
-  const char* mode = h->comm ? (h->comm->halo == HALO_NCCL ? "ranks+nccl-sendrecv"
-                                : h->comm->in_kernel ? "ranks+ipc-peer-stores+in-kernel-ring"
-                                                     : "ranks+ipc-peer-stores+wait/signal-kernels")
-                             : (h->slabs.size() > 1 ? "one-process+peer-stores" : "single-gpu");
-  snprintf(cfg, sizeof cfg, "vec=%d tpb=%d chunk=%d graph=%d pdl=%d fuse=%d slabs=%d halo=%s%s plane_stride=%lld",
-           h->vec, h->tpb, h->chunk, (int)(h->use_graph && h->world == 1),
-           (int)(h->use_pdl && h->world == 1), fused_ok(h) ? 2 : 1, h->world, mode, red,
-           h->slabs[0].ps);
+  char cfg[400], stream[96] = "";
+  const int S = stream_steps(h);
+  const bool multi = h->world > 1;
+  const char* red = (multi && h->reduce_per_step) ? " reduce=in-kernel-allreduce-per-step" : "";
+  const char* mode = !multi ? "single-gpu"
+                     : (h->comm && h->comm->halo == HALO_NCCL) ? "ranks+nccl-sendrecv"
+                     : h->comm ? ((S > 1 || h->ring_in_kernel) ? "ranks+ipc-peer-stores+in-kernel-ring"
+                                                              : "ranks+ipc-peer-stores+wait/signal-kernels")
+                               : ((S > 1 || h->ring_in_kernel) ? "one-process+peer-stores+in-kernel-ring"
+                                                              : "one-process+peer-stores+wait/signal-kernels");
+  if (S > 1) {
+    const StreamCfg& c = STREAM_CFGS[h->stream_cfg];
+    snprintf(stream, sizeof stream, " stream=tma(S=%d,nw=%d,stages=%d,blocks/sm=%d) tile=%dx%d",
+             c.s, c.nw, c.k0, c.minb, lbm::S_OUT_W, h->slabs[0].tile_h);
+  }
+  // graph replay and PDL apply to the one-step kernel on one GPU only
+  const bool one_step_only = S == 1 && !multi;
+  snprintf(cfg, sizeof cfg, "vec=%d tpb=%d chunk=%d graph=%d pdl=%d fuse=%d%s slabs=%d halo=%s%s plane_stride=%lld",
+           h->vec, h->tpb, h->chunk, (int)(h->use_graph && one_step_only), (int)(h->use_pdl && one_step_only),
+           S, stream, h->world, mode, red, h->slabs[0].ps);
   h->config = cfg;
 }
 
@@ -870,6 +1048,16 @@ lbm_lattice* new_lattice(const lbm_params* p, int world)
   return h;
 }
 
+void set_ring_mode(lbm_lattice* h)
+{
+  h->ring = h->world > 1 && !(h->comm && h->comm->halo == HALO_NCCL);
+  // Ring ordering inside the ONE-STEP kernel needs every row to start on its own 128-byte line (an
+  // interior block must not pull a stale copy of a ghost row's tail into L1 before the boundary
+  // block has seen the neighbour's flag); otherwise two tiny wait/signal launches bracket each step.
+  // (The streaming kernel reads through TMA, which bypasses L1, and always orders itself.)
+  h->ring_in_kernel = h->ring && (h->p.nx % 32 == 0) && !env_is("LBM_RING", "kernels");
+}
+
 int create_impl(lbm_lattice** out, const lbm_params* p, const int* obstacles, int first_device,
                 int nslab)
 {
@@ -878,10 +1066,12 @@ int create_impl(lbm_lattice** out, const lbm_params* p, const int* obstacles, in
   cudaGetDeviceCount(&ndev);
   if (nslab < 1 || first_device < 0 || first_device + nslab > ndev)
     return fail("lbm_create: %d GPU(s) requested from device %d but %d visible", nslab, first_device, ndev);
-  if (nslab > 1 && p->ny / nslab < 3)
-    return fail("lbm_create: %d rows cannot be split into %d slabs of >= 3 rows", p->ny, nslab);
+  if (nslab > 1 && p->ny / nslab < G)
+    return fail("lbm_create: %d rows cannot be split into %d slabs of >= %d rows", p->ny, nslab, G);
+  if (nslab > MAX_WORLD) return fail("lbm_create: at most %d slabs", MAX_WORLD);
 
   lbm_lattice* h = new_lattice(p, nslab);
+  set_ring_mode(h);
   const int nx = p->nx;
   h->slabs.resize(nslab);
   for (int k = 0; k < nslab; k++) {
@@ -889,17 +1079,20 @@ int create_impl(lbm_lattice** out, const lbm_params* p, const int* obstacles, in
     s.device = first_device + k;
     s.rank = k;
     lbm_slab_rows(p->ny, nslab, k, &s.y0, &s.rows);
-    if (create_slab(h, s, obstacles + (size_t)s.y0 * nx, &h->tot_cells)) { lbm_destroy(h); return 1; }
+    if (create_slab(h, s, obstacles, 0, p->ny, &h->tot_cells)) { lbm_destroy(h); return 1; }
   }
   for (int k = 0; k < nslab; k++) {
     Slab& s = h->slabs[k];
     Slab& lo = h->slabs[(k + nslab - 1) % nslab];
     Slab& hi = h->slabs[(k + 1) % nslab];
     wire_ghosts(s, nx, lo.base, lo.rows, lo.ps, hi.base, hi.ps);
+    for (int r = 0; r < nslab; r++) s.allred_peer[r] = h->slabs[r].allred;
     if (nslab > 1) {
       cudaSetDevice(s.device);
-      for (const Slab* nb : {&lo, &hi}) {
-        if (nb->device == s.device) continue;
+      for (int r = 0; r < nslab; r++) {
+        const Slab* nb = &h->slabs[r];
+        const bool neighbour = nb == &lo || nb == &hi;
+        if (nb->device == s.device || !(neighbour || h->reduce_per_step)) continue;
         int can = 0;
         cudaDeviceCanAccessPeer(&can, s.device, nb->device);
         if (!can) {
@@ -922,35 +1115,22 @@ int create_impl(lbm_lattice** out, const lbm_params* p, const int* obstacles, in
   return 0;
 }
 
-// one process per GPU: NCCL communicator, global cell count, IPC mapping of the two neighbours
+// one process per GPU: NCCL communicator, global cell count, IPC mapping of the other ranks
 int attach_comm(lbm_lattice* h, int rank, int world, const void* unique_id)
 {
   NcclApi* n = nccl_api();
   if (!n) return fail("lbm_create_rank: libnccl.so.2 could not be loaded (%s)", dlerror());
   if (!unique_id) return fail("lbm_create_rank: world > 1 needs an ncclUniqueId");
   Slab& s = h->slabs[0];
-  Comm* c = new Comm();
-  h->comm = c;
-  c->rank = rank;
-  c->world = world;
-  const char* halo = getenv("LBM_HALO");
-  c->halo = (halo && !strcmp(halo, "nccl")) ? HALO_NCCL : HALO_P2P;
-  const char* red = getenv("LBM_REDUCE");
-  c->per_step_allreduce = red && !strcmp(red, "step");
-  CK(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
-  CK(cudaEventCreateWithFlags(&c->ev_side, cudaEventDisableTiming));
+  Comm* c = h->comm;
   ncclUniqueId id;
   memcpy(&id, unique_id, sizeof id);
   NK(n->CommInitRank(&c->nccl, world, id, rank));
   CK(cudaMalloc(&c->scratch64, sizeof(long long) * 2));
-  CK(cudaMemset(c->scratch64, 0, sizeof(long long) * 2));
+  CK(cudaMemsetAsync(c->scratch64, 0, sizeof(long long) * 2, s.stream));
 
   // global number of fluid cells (d2q9-bgk.c:146-152 counts them over the whole grid)
-  long long* d_cnt = c->scratch64 + 1;
-  CK(cudaMemcpy(d_cnt, &h->tot_cells, sizeof(long long), cudaMemcpyHostToDevice));
-  NK(n->AllReduce(d_cnt, d_cnt, 1, ncclInt64, ncclSum, c->nccl, s.stream));
-  CK(cudaStreamSynchronize(s.stream));
-  CK(cudaMemcpy(&h->tot_cells, d_cnt, sizeof(long long), cudaMemcpyDeviceToHost));
+  if (comm_barrier(h, h->tot_cells, &h->tot_cells)) return 1;
 
   const int nx = h->p.nx;
   const int lo = (rank + world - 1) % world, hi = (rank + 1) % world;
@@ -974,25 +1154,30 @@ int attach_comm(lbm_lattice* h, int rank, int world, const void* unique_id)
   char* d_all = nullptr;
   const size_t hb = sizeof(cudaIpcMemHandle_t);
   CK(cudaMalloc(&d_all, hb * (world + 1)));
-  CK(cudaMemcpy(d_all + hb * world, &mine, hb, cudaMemcpyHostToDevice));
+  CK(cudaMemcpyAsync(d_all + hb * world, &mine, hb, cudaMemcpyHostToDevice, s.stream));
+  CK(cudaStreamSynchronize(s.stream));
   NK(n->AllGather(d_all + hb * world, d_all, hb, ncclChar, c->nccl, s.stream));
   CK(cudaStreamSynchronize(s.stream));
   std::vector<cudaIpcMemHandle_t> all(world);
   CK(cudaMemcpy(all.data(), d_all, hb * world, cudaMemcpyDeviceToHost));
   CK(cudaFree(d_all));
-  CK(cudaIpcOpenMemHandle(&c->peer_lo, all[lo], cudaIpcMemLazyEnablePeerAccess));
-  if (hi == lo) c->peer_hi = c->peer_lo;
-  else CK(cudaIpcOpenMemHandle(&c->peer_hi, all[hi], cudaIpcMemLazyEnablePeerAccess));
-
-  wire_ghosts(s, nx, (char*)c->peer_lo, lo_rows, lo_ps, (char*)c->peer_hi, hi_ps);
-  // my lower neighbour counts me as its UPPER neighbour (its sync[1]); the upper one as its LOWER
-  c->peer_lo_flag = reinterpret_cast<unsigned*>(reinterpret_cast<float*>(c->peer_lo) + 18 * lo_ps) + 1;
-  c->peer_hi_flag = reinterpret_cast<unsigned*>(reinterpret_cast<float*>(c->peer_hi) + 18 * hi_ps) + 0;
-  // Ring ordering inside the step kernel needs every row to start on its own 128-byte line (an
-  // interior block must not pull a stale copy of a ghost row's tail into L1 before the boundary
-  // block has seen the neighbour's flag); otherwise two tiny wait/signal launches bracket each step.
-  const char* ring = getenv("LBM_RING");
-  c->in_kernel = (nx % 32 == 0) && !(ring && !strcmp(ring, "kernels"));
+  c->peers.assign(world, nullptr);
+  for (int r = 0; r < world; r++) {
+    if (r == rank || !(r == lo || r == hi || h->reduce_per_step)) continue;
+    CK(cudaIpcOpenMemHandle(&c->peers[r], all[r], cudaIpcMemLazyEnablePeerAccess));
+  }
+  wire_ghosts(s, nx, (char*)c->peers[lo], lo_rows, lo_ps, (char*)c->peers[hi], hi_ps);
+  if (h->reduce_per_step) {
+    for (int r = 0; r < world; r++) {
+      int ry0, rrows;
+      lbm_slab_rows(h->p.ny, world, r, &ry0, &rrows);
+      s.allred_peer[r] = r == rank ? s.allred : allred_of((char*)c->peers[r], plane_stride(rrows, nx, h->pad), rrows, nx);
+    }
+  }
+  // obstacle flags of my boundary rows -> the neighbours' ghost rows (they mirror my rows)
+  lbm::flags_ghost_push_kernel<<<64, 256, 0, s.stream>>>(
+      s.flags, nx, s.rows, flags_of(s.lo_base, lo_ps) + (size_t)(G + lo_rows) * nx, flags_of(s.hi_base, hi_ps));
+  CK(cudaGetLastError());
   if (comm_barrier(h)) return 1;
   c->ready = true;
   return 0;
@@ -1031,16 +1216,24 @@ int lbm_create_rank(lbm_lattice** out, const lbm_params* params, const int* obst
   if (world == 1 && rank == 0) return create_impl(out, params, obstacles_slab, device, 1);
   if (common_checks(out, params, obstacles_slab)) return 1;
   if (world < 1 || rank < 0 || rank >= world) return fail("lbm_create_rank: rank %d of %d", rank, world);
-  if (params->ny / world < 3)
-    return fail("lbm_create_rank: %d rows cannot be split into %d slabs of >= 3 rows", params->ny, world);
+  if (world > MAX_WORLD) return fail("lbm_create_rank: at most %d ranks", MAX_WORLD);
+  if (params->ny / world < G)
+    return fail("lbm_create_rank: %d rows cannot be split into %d slabs of >= %d rows", params->ny, world, G);
   lbm_lattice* h = new_lattice(params, world);
+  h->comm = new Comm();
+  h->comm->rank = rank;
+  h->comm->world = world;
+  h->comm->halo = env_is("LBM_HALO", "nccl") ? HALO_NCCL : HALO_P2P;
+  if (h->comm->halo == HALO_NCCL) h->reduce_per_step = false;
+  if (h->stall_test) h->stall_test = env_int("LBM_TEST_RING_STALL", -1) == rank;
+  set_ring_mode(h);
   h->slabs.resize(1);
   Slab& s = h->slabs[0];
   s.device = device;
   s.rank = rank;
   lbm_slab_rows(params->ny, world, rank, &s.y0, &s.rows);
   h->host_y0 = s.y0;
-  if (create_slab(h, s, obstacles_slab, &h->tot_cells) || attach_comm(h, rank, world, nccl_unique_id)) {
+  if (create_slab(h, s, obstacles_slab, s.y0, s.rows, &h->tot_cells) || attach_comm(h, rank, world, nccl_unique_id)) {
     lbm_destroy(h);
     return 1;
   }
@@ -1076,12 +1269,9 @@ void lbm_destroy(lbm_lattice* h)
       n->AllReduce(c->scratch64, c->scratch64, 1, ncclInt64, ncclSum, c->nccl, s.stream);
       cudaStreamSynchronize(s.stream);
     }
-    if (c->peer_hi && c->peer_hi != c->peer_lo) cudaIpcCloseMemHandle(c->peer_hi);
-    if (c->peer_lo) cudaIpcCloseMemHandle(c->peer_lo);
+    for (void* p : c->peers)
+      if (p) cudaIpcCloseMemHandle(p);
     if (c->dummy_ghost) cudaFree(c->dummy_ghost);
-    if (c->step_sums) cudaFree(c->step_sums);
-    if (c->ev_side) cudaEventDestroy(c->ev_side);
-    if (c->side) cudaStreamDestroy(c->side);
     if (c->scratch64) cudaFree(c->scratch64);
     if (c->nccl && n) n->CommDestroy(c->nccl);
     delete c;
@@ -1090,13 +1280,12 @@ void lbm_destroy(lbm_lattice* h)
     cudaSetDevice(s.device);
     drop_graphs(s);
     if (s.base) cudaFree(s.base);
-    if (s.flags) cudaFree(s.flags);
     if (s.partials) cudaFree(s.partials);
     if (s.totals) cudaFree(s.totals);
     if (s.counter) cudaFree(s.counter);
+    if (s.macro) cudaFree(s.macro);
     if (s.ev_begin) cudaEventDestroy(s.ev_begin);
     if (s.ev_end) cudaEventDestroy(s.ev_end);
-    for (int i = 0; i < 2; i++) if (s.ev_step[i]) cudaEventDestroy(s.ev_step[i]);
     if (s.stream) cudaStreamDestroy(s.stream);
   }
   delete h;
@@ -1111,7 +1300,7 @@ int lbm_init_equilibrium(lbm_lattice* h)
   const float w2 = (float)((double)h->p.density / 36.0);
   for (auto& s : h->slabs) {
     CK(cudaSetDevice(s.device));
-    const long long cells = (long long)(s.rows + 2) * h->p.nx;
+    const long long cells = (long long)(s.rows + 2 * G) * h->p.nx;
     lbm::init_equilibrium_kernel<<<148 * 8, 256, 0, s.stream>>>(s.buf[h->cur], s.ps, cells, w0, w1, w2);
     CK(cudaGetLastError());
   }
@@ -1126,10 +1315,11 @@ int lbm_upload(lbm_lattice* h, const float* const cells[9])
   for (auto& s : h->slabs) {
     CK(cudaSetDevice(s.device));
     for (int k = 0; k < 9; k++)
-      CK(cudaMemcpyAsync(s.buf[h->cur] + k * s.ps + nx, cells[k] + (size_t)(s.y0 - h->host_y0) * nx,
+      CK(cudaMemcpyAsync(s.buf[h->cur] + k * s.ps + (size_t)G * nx, cells[k] + (size_t)(s.y0 - h->host_y0) * nx,
                          sizeof(float) * (size_t)s.rows * nx, cudaMemcpyHostToDevice, s.stream));
   }
-  return refresh_ghosts(h);
+  if (sync_all(h)) return 1;      // the ghost zones are refreshed at the start of the next run
+  return comm_barrier(h);
 }
 
 int lbm_download(lbm_lattice* h, float* const cells[9])
@@ -1139,7 +1329,7 @@ int lbm_download(lbm_lattice* h, float* const cells[9])
   for (auto& s : h->slabs) {
     CK(cudaSetDevice(s.device));
     for (int k = 0; k < 9; k++)
-      CK(cudaMemcpyAsync(cells[k] + (size_t)(s.y0 - h->host_y0) * nx, s.buf[h->cur] + k * s.ps + nx,
+      CK(cudaMemcpyAsync(cells[k] + (size_t)(s.y0 - h->host_y0) * nx, s.buf[h->cur] + k * s.ps + (size_t)G * nx,
                          sizeof(float) * (size_t)s.rows * nx, cudaMemcpyDeviceToHost, s.stream));
   }
   return sync_all(h);
@@ -1164,14 +1354,34 @@ int lbm_run(lbm_lattice* h, int iters, float* av_vels)
 
 int lbm_step(lbm_lattice* h, float* av_vel) { return lbm_run(h, 1, av_vel); }
 
+namespace {
+// sum of per-block partials of a whole-slab reduction kernel, over slabs and (rank mode) ranks
+int finish_scalar(lbm_lattice* h, double local, double* out)
+{
+  double total = local;
+  if (h->comm) {
+    Slab& s = h->slabs[0];
+    double* d = reinterpret_cast<double*>(h->comm->scratch64 + 1);
+    CK(cudaMemcpyAsync(d, &total, sizeof(double), cudaMemcpyHostToDevice, s.stream));
+    CK(cudaStreamSynchronize(s.stream));
+    NK(nccl_api()->AllReduce(d, d, 1, ncclDouble, ncclSum, h->comm->nccl, s.stream));
+    CK(cudaMemcpyAsync(&total, d, sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaStreamSynchronize(s.stream));
+  }
+  *out = total;
+  return 0;
+}
+}  // namespace
+
 int lbm_av_velocity(lbm_lattice* h, float* av_vel)
 {
   if (!h || !av_vel) return fail("null argument");
   double total = 0;
   for (auto& s : h->slabs) {
     CK(cudaSetDevice(s.device));
-    const int nblk = std::min(s.nblk, 148 * 8);
-    lbm::av_velocity_kernel<256><<<nblk, 256, 0, s.stream>>>(s.buf[h->cur], s.flags, s.ps, h->p.nx,
+    const int nblk = std::min(s.np, 148 * 8);
+    lbm::av_velocity_kernel<256><<<nblk, 256, 0, s.stream>>>(s.buf[h->cur] + (size_t)G * h->p.nx,
+                                                           s.flags + (size_t)G * h->p.nx, s.ps, h->p.nx,
                                                            s.rows, s.partials);
     CK(cudaGetLastError());
     std::vector<double> part((size_t)nblk);
@@ -1179,14 +1389,7 @@ int lbm_av_velocity(lbm_lattice* h, float* av_vel)
     CK(cudaStreamSynchronize(s.stream));
     for (double v : part) total += v;
   }
-  if (h->comm) {
-    Slab& s = h->slabs[0];
-    double* d = reinterpret_cast<double*>(h->comm->scratch64 + 1);
-    CK(cudaMemcpy(d, &total, sizeof(double), cudaMemcpyHostToDevice));
-    NK(nccl_api()->AllReduce(d, d, 1, ncclDouble, ncclSum, h->comm->nccl, s.stream));
-    CK(cudaStreamSynchronize(s.stream));
-    CK(cudaMemcpy(&total, d, sizeof(double), cudaMemcpyDeviceToHost));
-  }
+  if (finish_scalar(h, total, &total)) return 1;
   *av_vel = (float)(total / (double)h->tot_cells);
   return 0;
 }
@@ -1197,24 +1400,16 @@ int lbm_total_density(lbm_lattice* h, double* total_out)
   double total = 0;
   for (auto& s : h->slabs) {
     CK(cudaSetDevice(s.device));
-    const int nblk = std::min(s.nblk, 148 * 8);
-    lbm::total_density_kernel<256><<<nblk, 256, 0, s.stream>>>(s.buf[h->cur], s.ps, h->p.nx, s.rows, s.partials);
+    const int nblk = std::min(s.np, 148 * 8);
+    lbm::total_density_kernel<256><<<nblk, 256, 0, s.stream>>>(s.buf[h->cur] + (size_t)G * h->p.nx, s.ps,
+                                                             h->p.nx, s.rows, s.partials);
     CK(cudaGetLastError());
     std::vector<double> part((size_t)nblk);
     CK(cudaMemcpyAsync(part.data(), s.partials, sizeof(double) * nblk, cudaMemcpyDeviceToHost, s.stream));
     CK(cudaStreamSynchronize(s.stream));
     for (double v : part) total += v;
   }
-  if (h->comm) {
-    Slab& s = h->slabs[0];
-    double* d = reinterpret_cast<double*>(h->comm->scratch64 + 1);
-    CK(cudaMemcpy(d, &total, sizeof(double), cudaMemcpyHostToDevice));
-    NK(nccl_api()->AllReduce(d, d, 1, ncclDouble, ncclSum, h->comm->nccl, s.stream));
-    CK(cudaStreamSynchronize(s.stream));
-    CK(cudaMemcpy(&total, d, sizeof(double), cudaMemcpyDeviceToHost));
-  }
-  *total_out = total;
-  return 0;
+  return finish_scalar(h, total, total_out);
 }
 
 int lbm_macroscopic(lbm_lattice* h, float* ux, float* uy, float* speed, float* pressure)
@@ -1224,20 +1419,17 @@ int lbm_macroscopic(lbm_lattice* h, float* ux, float* uy, float* speed, float* p
   for (auto& s : h->slabs) {
     CK(cudaSetDevice(s.device));
     const size_t n = (size_t)s.rows * nx;
-    float* scratch = nullptr;
-    CK(cudaMalloc(&scratch, sizeof(float) * 4 * n));
-    lbm::macroscopic_kernel<<<148 * 8, 256, 0, s.stream>>>(s.buf[h->cur], s.flags, s.ps, nx, s.rows,
-                                                         h->p.density, scratch, scratch + n,
-                                                         scratch + 2 * n, scratch + 3 * n);
+    if (!s.macro) CK(cudaMalloc(&s.macro, sizeof(float) * 4 * n));     // kept for the next call
+    lbm::macroscopic_kernel<<<148 * 8, 256, 0, s.stream>>>(s.buf[h->cur] + (size_t)G * nx, s.flags + (size_t)G * nx,
+                                                         s.ps, nx, s.rows, h->p.density, s.macro, s.macro + n,
+                                                         s.macro + 2 * n, s.macro + 3 * n);
     CK(cudaGetLastError());
     float* outs[4] = {ux, uy, speed, pressure};
     for (int k = 0; k < 4; k++)
-      CK(cudaMemcpyAsync(outs[k] + (size_t)(s.y0 - h->host_y0) * nx, scratch + k * n, sizeof(float) * n,
+      CK(cudaMemcpyAsync(outs[k] + (size_t)(s.y0 - h->host_y0) * nx, s.macro + k * n, sizeof(float) * n,
                          cudaMemcpyDeviceToHost, s.stream));
-    CK(cudaStreamSynchronize(s.stream));
-    CK(cudaFree(scratch));
   }
-  return 0;
+  return sync_all(h);
 }
 
 double lbm_last_run_ms(const lbm_lattice* h) { return h ? h->last_ms : 0.0; }

@@ -27,6 +27,7 @@ namespace lbm {
 constexpr unsigned FULL_MASK = 0xffffffffu;
 constexpr int FLAG_OBSTACLE = 1;   // cell is blocked (d2q9-bgk.c:627)
 constexpr int FLAG_ACCEL    = 2;   // fluid cell of global row ny-2 (kernels.cl:21,29)
+constexpr int GHOST = 4;           // ghost rows below and above a slab's owned rows (all nine planes)
 
 // system-scope flag accesses for the cross-GPU ring ordering
 __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p)
@@ -41,13 +42,62 @@ __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v)
 }
 // bounded spin until *flag >= want (wrap-safe); gives up after ~4 s of SM clocks and raises
 // *timed_out instead of hanging the GPU -- the host turns that into an error
+// (once the flag is raised later waits give up at once: a dead neighbour costs one time-out, not one per launch)
 __device__ __forceinline__ void spin_until(const unsigned* flag, unsigned want, unsigned* timed_out)
 {
   const long long t0 = clock64();
   while ((int)(ld_acquire_sys(flag) - want) < 0) {
+    if (*reinterpret_cast<volatile unsigned*>(timed_out) != 0u) break;
     if (clock64() - t0 > 8000000000LL) { *timed_out = 1u; break; }
     __nanosleep(100);
   }
+}
+
+// LBM_REDUCE=step -- the north-star's per-step allreduce of the speed sum (it replaces the serial
+// host sum d2q9-bgk.c:416-423), done by the step kernel itself: the last block of a launch to
+// finish adds up the launch's per-block partials in a fixed order and stores the slab total of
+// each timestep into EVERY rank's table (peer stores over NVLink); a rank then adds the table's
+// rows in rank order.  No collective launch, no host involvement, deterministic.
+constexpr int MAX_REDUCE_WORLD = 16;
+struct StepReduce {
+  double*   peer[MAX_REDUCE_WORLD];   // every rank's table [world][cap] (own included), null = off
+  int       world, rank, cap;
+  int       slot;                     // table column of this launch's first timestep
+  unsigned* ticket;                   // blocks of this launch that are done
+};
+
+// called by every thread of every block after the block's partials are written.  partials:
+// [nsteps][stride], `count` valid entries per step.  scratch: >= NT doubles of shared memory.
+template <int NT>
+__device__ __forceinline__ void last_block_allreduce(const StepReduce& R, const double* partials, int stride,
+                                                     int count, int nsteps, double* scratch)
+{
+  if (R.peer[0] == nullptr) return;
+  __shared__ int is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = atomicAdd(R.ticket, 1u) == gridDim.x - 1u;
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  for (int s = 0; s < nsteps; s++) {
+    double v = 0.0;
+    for (int i = threadIdx.x; i < count; i += NT) v += __ldcg(partials + (long long)s * stride + i);
+    scratch[threadIdx.x] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      double t = 0.0;
+      for (int i = threadIdx.x; i < NT; i += 32) t += scratch[i];
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) t += __shfl_down_sync(FULL_MASK, t, off);
+      if (threadIdx.x == 0) {
+        const int col = (R.slot + s) % R.cap;
+        for (int r = 0; r < R.world; r++) R.peer[r][(long long)R.rank * R.cap + col] = t;
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { *R.ticket = 0u; __threadfence_system(); }
 }
 
 struct StepArgs {
@@ -63,12 +113,6 @@ struct StepArgs {
   int            fuse_accel; // apply the NEXT step's accelerate_flow to the values being stored
   float*         ghost_lo[3];// row base receiving planes 4,7,8 of the first owned row
   float*         ghost_hi[3];// row base receiving planes 2,5,6 of the last owned row
-  // source and destination may be different objects (the fix-up of a two-step pass reads a
-  // 3-row strip and writes a slab row): destination plane stride, and the float offset of the
-  // destination (and flag) row relative to the source row; which ghost pushes this launch owns
-  long long      ps_dst;
-  long long      dst_delta;
-  int            push;       // bit 0: row 1 -> ghost_lo, bit 1: row `rows` -> ghost_hi
   double*        partials;   // [gridDim.x] per-block sums of cell speeds for this step
   // one-process-per-GPU ring ordering done by the boundary blocks themselves (null = not used):
   const unsigned* ring_in;   // [0] steps finished by my lower neighbour's top row, [1] by my upper's bottom row
@@ -79,6 +123,7 @@ struct StepArgs {
   unsigned       ring_step;  // number of steps every rank has completed before this one
   int            rot;        // block-id rotation: the blocks holding the last row run first
   int            nb_lo, nb_hi;// how many blocks touch the first / the last owned row
+  StepReduce     red;        // LBM_REDUCE=step (peer[0] == null: off)
 };
 
 // ---- vector access helpers ---------------------------------------------------------------
@@ -199,8 +244,8 @@ lbm_step_kernel(const __grid_constant__ StepArgs A)
     // my ghost row (my input) have landed and it no longer reads the ghost row I will overwrite.
     const unsigned first = vb * TPB;
     const unsigned last = min(first + TPB, (unsigned)A.nvec) - 1u;
-    ring_lo = first < (unsigned)A.nxv && (A.push & 1);      // a strip launch owns one side only
-    ring_hi = last >= (unsigned)(A.rows - 1) * (unsigned)A.nxv && (A.push & 2);
+    ring_lo = first < (unsigned)A.nxv;
+    ring_hi = last >= (unsigned)(A.rows - 1) * (unsigned)A.nxv;
     if (ring_lo || ring_hi) {
       if (threadIdx.x == 0) {
         if (ring_lo) spin_until(A.ring_in + 0, A.ring_step, A.ring_timeout);
@@ -237,7 +282,7 @@ lbm_step_kernel(const __grid_constant__ StepArgs A)
   float f[9][VEC];
   float v1[VEC], v3[VEC], v5[VEC], v6[VEC], v7[VEC], v8[VEC];
   float e1 = 0.f, e3 = 0.f, e5 = 0.f, e6 = 0.f, e7 = 0.f, e8 = 0.f;
-  const unsigned flags = ld_flags<VEC>(A.flags + row_mid + A.dst_delta + x);   // constant data: may precede the wait
+  const unsigned flags = ld_flags<VEC>(A.flags + row_mid + x);   // constant data: may precede the wait
   // everything below reads what the previous step wrote (and overwrites what it read)
   asm volatile("griddepcontrol.wait;" ::: "memory");
   ld_vec<VEC>(s + row_mid + x, f[0]);
@@ -302,15 +347,15 @@ lbm_step_kernel(const __grid_constant__ StepArgs A)
   }
 
   if (active) {
-    float* d = A.dst + row_mid + A.dst_delta + x;
+    float* d = A.dst + row_mid + x;
 #pragma unroll
-    for (int k = 0; k < 9; k++) st_vec<VEC>(d + k * A.ps_dst, f[k]);
-    if (r == 1 && (A.push & 1)) {            // my south neighbour pulls 4,7,8 from this row
+    for (int k = 0; k < 9; k++) st_vec<VEC>(d + k * ps, f[k]);
+    if (r == 1) {            // my south neighbour pulls 4,7,8 from this row
       st_vec<VEC>(A.ghost_lo[0] + x, f[4]);
       st_vec<VEC>(A.ghost_lo[1] + x, f[7]);
       st_vec<VEC>(A.ghost_lo[2] + x, f[8]);
     }
-    if (r == A.rows && (A.push & 2)) {       // my north neighbour pulls 2,5,6 from this row
+    if (r == A.rows) {       // my north neighbour pulls 2,5,6 from this row
       st_vec<VEC>(A.ghost_hi[0] + x, f[2]);
       st_vec<VEC>(A.ghost_hi[1] + x, f[5]);
       st_vec<VEC>(A.ghost_hi[2] + x, f[6]);
@@ -340,52 +385,13 @@ lbm_step_kernel(const __grid_constant__ StepArgs A)
 
   const double total = block_sum<TPB>(speed_sum);
   if (threadIdx.x == 0) A.partials[vb] = total;
+  if (A.red.peer[0] != nullptr) {
+    __shared__ double red_scratch[TPB];
+    last_block_allreduce<TPB>(A.red, A.partials, 0, (int)gridDim.x, 1, red_scratch);
+  }
 }
 
-// ---- two timesteps per pass (temporal blocking) ------------------------------------------------
-// One block = one tile: it pulls the populations of time t from HBM exactly as lbm_step_kernel
-// does, relaxes F_RA rows x 128 columns to time t+1 INTO SHARED MEMORY, and from there relaxes the
-// inner F_RA-2 rows x 120 columns to time t+2, which is what it stores (default: 7 warps, F_RA = 14).  Per two lattice updates a
-// cell costs one (slightly amplified) read and one write instead of two of each; the arithmetic
-// per cell and step is the same f32-strict sequence, so the state stays bit-identical.
-//
-// Ghost depth stays 1: with ghost rows valid at time t a slab can compute t+1 on all of its rows
-// but t+2 only on rows 2..rows-1.  Rows 1 and `rows` of time t+2 need the neighbours' t+1 boundary
-// rows; the pass therefore also writes the t+1 populations of rows 1, 2, rows-1, rows into two 3-row
-// "strips" (own rows + a ghost row that the NEIGHBOUR's pass fills over NVLink), and two tiny
-// launches of lbm_step_kernel on those strips (rows = 1) finish rows 1 and `rows` and push the t+2
-// ghost rows as usual.  strip_lo rows: [neighbour's last row | my row 1 | my row 2];
-// strip_hi rows: [my row rows-1 | my row rows | neighbour's first row].
-constexpr int F_TX = 120;   // output columns per tile (30 lanes x 4)
-// tile height and block size are template parameters (RA = rows relaxed to t+1 = output rows + one
-// above and below); shared memory = 9 planes x RA rows x 32 lanes x 16 B
-constexpr int fused_smem(int ra) { return 9 * ra * 32 * 16; }
-
-struct FusedArgs {
-  const float*   src;
-  float*         dst;
-  const uint8_t* flags;
-  long long      ps;
-  int            nx, rows, tiles_x, tiles_y;
-  float          omega, a1, a2;
-  int            fuse_b;       // apply the following step's acceleration to the t+2 values
-  float*         strip_lo;     // 9 planes, stride pse, 3 rows of nx
-  float*         strip_hi;
-  long long      pse;
-  float*         nb_lo[3];     // lower neighbour's strip_hi row 2: planes 4,7,8 of my row 1 (t+1)
-  float*         nb_hi[3];     // upper neighbour's strip_lo row 0: planes 2,5,6 of my row `rows` (t+1)
-  double*        partials_a;   // [tiles] speed sums of step t+1
-  double*        partials_b;   // [tiles] speed sums of step t+2 (rows 2..rows-1)
-  // ring ordering by the bottom / top tiles themselves (null = ordered by separate launches)
-  const unsigned* ring_in;
-  unsigned*      ring_out_lo;
-  unsigned*      ring_out_hi;
-  unsigned*      ring_tickets;
-  unsigned*      ring_timeout;
-  unsigned       ring_step;
-  int            rot;          // tiles rotated to the front of the grid (the top tile row)
-};
-
+// ---- helpers shared with the streaming kernel (lbm_stream.cuh) ----------------------------------
 // relax the 4 cells a thread holds; speeds are accumulated only when `count`
 template <bool FAST>
 __device__ __forceinline__ double relax_vec4(float (&f)[9][4], unsigned flags, float omega, float a1,
@@ -431,179 +437,13 @@ __device__ __forceinline__ double relax_vec4(float (&f)[9][4], unsigned flags, f
 
 __device__ __forceinline__ float4 f4(const float (&v)[4]) { return make_float4(v[0], v[1], v[2], v[3]); }
 
-template <int F_TPB, int F_RA, int MINB>
-__global__ void __launch_bounds__(F_TPB, MINB)
-lbm_fused2_kernel(const __grid_constant__ FusedArgs A)
-{
-  constexpr int F_TY = F_RA - 2;
-  extern __shared__ float4 tile[];                 // [9][F_RA][32]
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // the top row of tiles is rotated to the front of the grid, the bottom row follows: both write the
-  // t+1 boundary rows the neighbours' fix-ups need, so those are on the wire first
-  const unsigned vb = A.rot == 0 ? blockIdx.x
-                      : (blockIdx.x < (unsigned)A.rot ? gridDim.x - A.rot + blockIdx.x : blockIdx.x - A.rot);
-  const int bx = (int)(vb % (unsigned)A.tiles_x), by = (int)(vb / (unsigned)A.tiles_x);
-  bool ring_lo = false, ring_hi = false;
-  if (A.ring_in != nullptr) {
-    // before this pass the neighbour's fix-up of the previous pass must be done: it wrote my ghost
-    // row (input of the bottom / top tiles) and has read the strip row those tiles overwrite
-    ring_lo = by == 0;
-    ring_hi = by == A.tiles_y - 1;
-    if (ring_lo || ring_hi) {
-      if (threadIdx.x == 0) {
-        if (ring_lo) spin_until(A.ring_in + 0, A.ring_step, A.ring_timeout);
-        if (ring_hi) spin_until(A.ring_in + 1, A.ring_step, A.ring_timeout);
-      }
-      __syncthreads();
-    }
-  }
-  const int oy0 = 2 + F_TY * by;                   // first output row (storage index)
-  const int oy1 = min(oy0 + F_TY, A.rows);         // one past the last output row (<= rows-1)
-  const int ay0 = oy0 - 1;                         // first row relaxed to t+1
-  const int nra = oy1 - oy0 + 2;
-  const int xu = F_TX * bx - 4 + 4 * lane;         // my first column before the periodic wrap
-  const int x = xu < 0 ? xu + A.nx : (xu >= A.nx ? xu - A.nx : xu);
-  const int xw = (x == 0) ? A.nx - 1 : x - 1;
-  const int xe = (x + 4 == A.nx) ? 0 : x + 4;
-  const bool mine = lane >= 1 && lane <= 30 && xu < A.nx;   // columns this tile stores / accounts for
-  const long long ps = A.ps;
-  double sum_a = 0.0, sum_b = 0.0;
-
-  // ---- step t -> t+1: rows ay0 .. ay0+nra-1, all 128 columns, into shared memory
-  for (int ar = warp; ar < nra; ar += F_TPB / 32) {
-    const int r = ay0 + ar;
-    const long long row_mid = (long long)r * A.nx;
-    const long long row_lo = row_mid - A.nx, row_hi = row_mid + A.nx;
-    const float* s = A.src;
-    const float* p1 = s + 1 * ps + row_mid; const float* p3 = s + 3 * ps + row_mid;
-    const float* p5 = s + 5 * ps + row_lo;  const float* p6 = s + 6 * ps + row_lo;
-    const float* p7 = s + 7 * ps + row_hi;  const float* p8 = s + 8 * ps + row_hi;
-    float f[9][4];
-    float v1[4], v3[4], v5[4], v6[4], v7[4], v8[4];
-    float e1 = 0.f, e3 = 0.f, e5 = 0.f, e6 = 0.f, e7 = 0.f, e8 = 0.f;
-    ld_vec<4>(s + row_mid + x, f[0]);
-    ld_vec<4>(p1 + x, v1);
-    ld_vec<4>(s + 2 * ps + row_lo + x, f[2]);
-    ld_vec<4>(p3 + x, v3);
-    ld_vec<4>(s + 4 * ps + row_hi + x, f[4]);
-    ld_vec<4>(p5 + x, v5);
-    ld_vec<4>(p6 + x, v6);
-    ld_vec<4>(p7 + x, v7);
-    ld_vec<4>(p8 + x, v8);
-    const unsigned flags = ld_flags<4>(A.flags + row_mid + x);
-    if (lane == 0)  { e1 = p1[xw]; e5 = p5[xw]; e8 = p8[xw]; }
-    if (lane == 31) { e3 = p3[xe]; e6 = p6[xe]; e7 = p7[xe]; }
-    {
-      const float l1 = __shfl_up_sync(FULL_MASK, v1[3], 1);
-      const float l5 = __shfl_up_sync(FULL_MASK, v5[3], 1);
-      const float l8 = __shfl_up_sync(FULL_MASK, v8[3], 1);
-      const float r3 = __shfl_down_sync(FULL_MASK, v3[0], 1);
-      const float r6 = __shfl_down_sync(FULL_MASK, v6[0], 1);
-      const float r7 = __shfl_down_sync(FULL_MASK, v7[0], 1);
-      f[1][0] = lane == 0 ? e1 : l1;  f[5][0] = lane == 0 ? e5 : l5;  f[8][0] = lane == 0 ? e8 : l8;
-      f[3][3] = lane == 31 ? e3 : r3; f[6][3] = lane == 31 ? e6 : r6; f[7][3] = lane == 31 ? e7 : r7;
-#pragma unroll
-      for (int i = 1; i < 4; i++) { f[1][i] = v1[i - 1]; f[5][i] = v5[i - 1]; f[8][i] = v8[i - 1]; }
-#pragma unroll
-      for (int i = 0; i < 3; i++) { f[3][i] = v3[i + 1]; f[6][i] = v6[i + 1]; f[7][i] = v7[i + 1]; }
-    }
-    // every cell of the slab is accounted for once at t+1: by the tile whose output row it is, rows
-    // 1 and `rows` (relaxed here only as halo rows) by the bottom and the top tile
-    const bool count = mine && ((ar >= 1 && ar <= nra - 2) || r == 1 || r == A.rows);
-    // step t+2 always follows inside this pass, so its acceleration is applied here
-    sum_a += relax_vec4<false>(f, flags, A.omega, A.a1, A.a2, true, count);
-#pragma unroll
-    for (int k = 0; k < 9; k++) tile[(k * F_RA + ar) * 32 + lane] = f4(f[k]);
-
-    if (mine) {   // t+1 boundary rows for the fix-up launches (own strips, neighbours' ghost rows)
-      if (r == 1) {
-#pragma unroll
-        for (int k = 0; k < 9; k++) st_vec<4>(A.strip_lo + k * A.pse + A.nx + x, f[k]);
-        st_vec<4>(A.nb_lo[0] + x, f[4]); st_vec<4>(A.nb_lo[1] + x, f[7]); st_vec<4>(A.nb_lo[2] + x, f[8]);
-      }
-      if (r == 2) {
-        st_vec<4>(A.strip_lo + 4 * A.pse + 2 * A.nx + x, f[4]);
-        st_vec<4>(A.strip_lo + 7 * A.pse + 2 * A.nx + x, f[7]);
-        st_vec<4>(A.strip_lo + 8 * A.pse + 2 * A.nx + x, f[8]);
-      }
-      if (r == A.rows - 1) {
-        st_vec<4>(A.strip_hi + 2 * A.pse + x, f[2]);
-        st_vec<4>(A.strip_hi + 5 * A.pse + x, f[5]);
-        st_vec<4>(A.strip_hi + 6 * A.pse + x, f[6]);
-      }
-      if (r == A.rows) {
-#pragma unroll
-        for (int k = 0; k < 9; k++) st_vec<4>(A.strip_hi + k * A.pse + A.nx + x, f[k]);
-        st_vec<4>(A.nb_hi[0] + x, f[2]); st_vec<4>(A.nb_hi[1] + x, f[5]); st_vec<4>(A.nb_hi[2] + x, f[6]);
-      }
-    }
-  }
-  __syncthreads();
-
-  // ---- step t+1 -> t+2: output rows from shared memory (lanes 0 and 31 only feed their neighbours)
-  for (int orow = oy0 + warp; orow < oy1; orow += F_TPB / 32) {
-    const int ar = orow - ay0;
-    const long long row_mid = (long long)orow * A.nx;
-    const unsigned flags = ld_flags<4>(A.flags + row_mid + x);
-    const float4 q0 = tile[(0 * F_RA + ar) * 32 + lane];
-    const float4 q1 = tile[(1 * F_RA + ar) * 32 + lane];
-    const float4 q3 = tile[(3 * F_RA + ar) * 32 + lane];
-    const float4 q2 = tile[(2 * F_RA + ar - 1) * 32 + lane];
-    const float4 q5 = tile[(5 * F_RA + ar - 1) * 32 + lane];
-    const float4 q6 = tile[(6 * F_RA + ar - 1) * 32 + lane];
-    const float4 q4 = tile[(4 * F_RA + ar + 1) * 32 + lane];
-    const float4 q7 = tile[(7 * F_RA + ar + 1) * 32 + lane];
-    const float4 q8 = tile[(8 * F_RA + ar + 1) * 32 + lane];
-    float f[9][4];
-    f[0][0] = q0.x; f[0][1] = q0.y; f[0][2] = q0.z; f[0][3] = q0.w;
-    f[2][0] = q2.x; f[2][1] = q2.y; f[2][2] = q2.z; f[2][3] = q2.w;
-    f[4][0] = q4.x; f[4][1] = q4.y; f[4][2] = q4.z; f[4][3] = q4.w;
-    f[1][0] = __shfl_up_sync(FULL_MASK, q1.w, 1); f[1][1] = q1.x; f[1][2] = q1.y; f[1][3] = q1.z;
-    f[5][0] = __shfl_up_sync(FULL_MASK, q5.w, 1); f[5][1] = q5.x; f[5][2] = q5.y; f[5][3] = q5.z;
-    f[8][0] = __shfl_up_sync(FULL_MASK, q8.w, 1); f[8][1] = q8.x; f[8][2] = q8.y; f[8][3] = q8.z;
-    f[3][3] = __shfl_down_sync(FULL_MASK, q3.x, 1); f[3][0] = q3.y; f[3][1] = q3.z; f[3][2] = q3.w;
-    f[6][3] = __shfl_down_sync(FULL_MASK, q6.x, 1); f[6][0] = q6.y; f[6][1] = q6.z; f[6][2] = q6.w;
-    f[7][3] = __shfl_down_sync(FULL_MASK, q7.x, 1); f[7][0] = q7.y; f[7][1] = q7.z; f[7][2] = q7.w;
-    sum_b += relax_vec4<false>(f, flags, A.omega, A.a1, A.a2, A.fuse_b != 0, mine);
-    if (mine) {
-      float* d = A.dst + row_mid + x;
-#pragma unroll
-      for (int k = 0; k < 9; k++) st_vec<4>(d + k * ps, f[k]);
-    }
-  }
-
-  if (ring_lo || ring_hi) {
-    // my t+1 boundary rows are in the neighbour's strip: publish "phase ring_step done" per side
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      if (ring_lo && atomicAdd(A.ring_tickets + 0, 1u) == (unsigned)A.tiles_x - 1u) {
-        A.ring_tickets[0] = 0u;
-        __threadfence_system();
-        st_release_sys(A.ring_out_lo, A.ring_step + 1u);
-      }
-      if (ring_hi && atomicAdd(A.ring_tickets + 1, 1u) == (unsigned)A.tiles_x - 1u) {
-        A.ring_tickets[1] = 0u;
-        __threadfence_system();
-        st_release_sys(A.ring_out_hi, A.ring_step + 1u);
-      }
-    }
-  }
-
-  const double ta = block_sum<F_TPB>(sum_a);
-  __syncthreads();
-  const double tb = block_sum<F_TPB>(sum_b);
-  if (threadIdx.x == 0) { A.partials_a[vb] = ta; A.partials_b[vb] = tb; }
-}
-
 // ---- small kernels ---------------------------------------------------------------------------
 
 // stand-alone accelerate_flow (kernels.cl:7-42) on storage row `r` of a buffer; used for the first
-// step of a run (every later step gets it from the previous step's epilogue).  Also refreshes the
-// ghost copies if that row happens to be a slab boundary row.
+// step of a run (every later step gets it from the previous step's epilogue).  The ghost zones are
+// refreshed right after it, so it touches the owned row only.
 __global__ void accelerate_row_kernel(float* buf, const uint8_t* flags, long long ps, int nx, int r,
-                                      int rows, float a1, float a2, float* glo7, float* glo8,
-                                      float* ghi5, float* ghi6)
+                                      float a1, float a2)
 {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   if (x >= nx) return;
@@ -614,21 +454,7 @@ __global__ void accelerate_row_kernel(float* buf, const uint8_t* flags, long lon
   if (__fsub_rn(*f3, a1) > 0.0f && __fsub_rn(*f6, a2) > 0.0f && __fsub_rn(*f7, a2) > 0.0f) {
     *f1 = __fadd_rn(*f1, a1); *f5 = __fadd_rn(*f5, a2); *f8 = __fadd_rn(*f8, a2);
     *f3 = __fsub_rn(*f3, a1); *f6 = __fsub_rn(*f6, a2); *f7 = __fsub_rn(*f7, a2);
-    if (r == 1)    { glo7[x] = *f7; glo8[x] = *f8; }
-    if (r == rows) { ghi5[x] = *f5; ghi6[x] = *f6; }
   }
-}
-
-// copy the boundary rows of a buffer into the neighbours' ghost rows (after upload / init)
-__global__ void halo_push_kernel(const float* buf, long long ps, int nx, int rows,
-                                 float* lo4, float* lo7, float* lo8,
-                                 float* hi2, float* hi5, float* hi6)
-{
-  const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  if (x >= nx) return;
-  const long long first = (long long)nx + x, last = (long long)rows * nx + x;
-  lo4[x] = buf[4 * ps + first]; lo7[x] = buf[7 * ps + first]; lo8[x] = buf[8 * ps + first];
-  hi2[x] = buf[2 * ps + last];  hi5[x] = buf[5 * ps + last];  hi6[x] = buf[6 * ps + last];
 }
 
 // initial equilibrium fill on the device (d2q9-bgk.c:573-594), ghost rows included
@@ -645,19 +471,17 @@ __global__ void init_equilibrium_kernel(float* buf, long long ps, long long cell
   }
 }
 
-// second stage of the average-velocity reduction: block s sums the nblk partials of step s in a
+// second stage of the average-velocity reduction: block s sums the `count` partials of step s in a
 // fixed order and writes the slab's speed total for that step (divided later by tot_cells).
-// `counter` holds the index of the first step of this chunk inside `totals`.
-// `stride` = partial slots per step; steps with an even / odd index in the chunk hold
-// count_even / count_odd valid partials (they differ only in two-step passes).
-__global__ void reduce_partials_kernel(const double* partials, int stride, int count_even, int count_odd,
-                                       double* totals, const long long* counter)
+// `counter` holds the index of the first step of this chunk inside `totals`; `stride` = partial
+// slots per step.
+__global__ void reduce_partials_kernel(const double* partials, int stride, int count, double* totals,
+                                       const long long* counter)
 {
   __shared__ double sm[256];
   const double* p = partials + (long long)blockIdx.x * stride;
-  const int nblk = (blockIdx.x & 1) ? count_odd : count_even;
   double v = 0.0;
-  for (int i = threadIdx.x; i < nblk; i += 256) v += p[i];
+  for (int i = threadIdx.x; i < count; i += 256) v += p[i];
   sm[threadIdx.x] = v;
   __syncthreads();
   for (int off = 128; off > 0; off >>= 1) {
@@ -680,7 +504,7 @@ av_velocity_kernel(const float* buf, const uint8_t* flags, long long ps, int nx,
   const long long stride = (long long)gridDim.x * TPB;
   double acc = 0.0;
   for (long long i = (long long)blockIdx.x * TPB + threadIdx.x; i < n; i += stride) {
-    const long long q = i + nx;                 // skip the lower ghost row
+    const long long q = i;                      // buf / flags point at the first owned row
     if (flags[q] & FLAG_OBSTACLE) continue;
     float t[9];
 #pragma unroll
@@ -709,7 +533,7 @@ total_density_kernel(const float* buf, long long ps, int nx, int rows, double* p
   const long long stride = (long long)gridDim.x * TPB;
   double acc = 0.0;
   for (long long i = (long long)blockIdx.x * TPB + threadIdx.x; i < n; i += stride) {
-    const long long q = i + nx;
+    const long long q = i;
 #pragma unroll
     for (int k = 0; k < 9; k++) acc += (double)buf[k * ps + q];
   }
@@ -726,7 +550,7 @@ __global__ void macroscopic_kernel(const float* buf, const uint8_t* flags, long 
   const long long n = (long long)rows * nx;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const long long q = i + nx;
+    const long long q = i;
     if (flags[q] & FLAG_OBSTACLE) {
       ux_out[i] = 0.0f; uy_out[i] = 0.0f; u_out[i] = 0.0f;
       p_out[i] = __fmul_rn(density, C_SQ);

@@ -200,7 +200,7 @@ def test_full_size_channel_properties(lbm):
     ob = cases.channel(nx, ny, rows=(0, ny))
     lat = lbm.Lattice(nx, ny, 0.1, 0.005, 1.85, ob)
     try:
-        assert "fuse=2" in lat.config          # HBM-streaming slab: two timesteps per pass by default
+        assert "fuse=2" in lat.config and "stream=tma" in lat.config   # HBM-streaming slab: two timesteps per pass
         lat.init_equilibrium()
         av = lat.run(12, f64=True)
         m = lat.macroscopic()
@@ -285,7 +285,7 @@ def test_one_process_per_gpu_bit_exact(lbm, world, halo, nx):
     if halo == "p2p-kernels":
         env["LBM_RING"] = "kernels"
     if halo == "p2p-allreduce":
-        env["LBM_REDUCE"] = "step"      # one 8-byte ncclAllReduce per timestep (north-star wording)
+        env["LBM_REDUCE"] = "step"      # per-step allreduce of the speed sum (north-star wording), done in-kernel
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
            os.path.join(cases.ROOT, "tools", "multirank_check.py"), "--nx", str(nx), "--ny", "100",
@@ -295,7 +295,7 @@ def test_one_process_per_gpu_bit_exact(lbm, world, halo, nx):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "-> OK" in r.stdout
     want = {"nccl": "nccl-sendrecv", "p2p-kernels": "wait/signal-kernels",
-            "p2p-allreduce": "reduce=allreduce-per-step",
+            "p2p-allreduce": "reduce=in-kernel-allreduce-per-step",
             "p2p": "in-kernel-ring" if nx % 32 == 0 else "wait/signal-kernels"}[halo]
     assert want in r.stdout
 
@@ -369,33 +369,68 @@ def test_executable_on_two_gpus(lbm, tmp_path):
     assert np.max(np.abs(outs[1][1] - outs[2][1]) / outs[1][1]) <= 1.2e-7
 
 
-# ---- two timesteps per pass (LBM_FUSE=2) --------------------------------------------------------
-FUSED_SIZES = [(128, 128), (256, 20), (1024, 12), (512, 37), (136, 9), (1000, 33), (248, 4), (2048, 70),
-               (16384, 19)]
+# ---- S timesteps per pass: the TMA / mbarrier streaming kernel (LBM_FUSE=2|3|4) --------------------
+# widths: one strip, several strips, a last strip of 8 / 16 / 64 columns (16384 = 136 * 120 + 64), widths
+# that are a multiple of 16 but not of 32 or 120; heights: one short tile, ragged last tile, ny = 16
+# (the minimum: 4 ghost rows on either side of every slab are recomputed from the neighbour's rows)
+STREAM_SIZES = [(128, 128), (256, 20), (1024, 16), (512, 37), (144, 33), (1008, 33), (240, 16), (2048, 70),
+                (16384, 19)]
 
 
-@pytest.mark.parametrize("nx,ny", FUSED_SIZES)
-@pytest.mark.parametrize("iters", [2, 7, 40])
-def test_two_step_passes_bit_exact(lbm, nx, ny, iters, monkeypatch):
-    """temporal blocking through shared-memory tiles + strip fix-ups: same arithmetic per cell and
-    step, so still bit-identical to the oracle; odd counts end with one ordinary step"""
-    monkeypatch.setenv("LBM_FUSE", "2")
-    monkeypatch.setenv("LBM_CHUNK", "8")
-    case = cases.random_case(nx, ny, seed=nx + 3 * ny, walls=(ny > 8))
-    f0 = cases.perturbed_state(case, seed=nx)
+def _run_and_compare(lbm, case, f0, iters, more=5):
     o = Oracle("f32b200", case)
     f = f0.copy()
     av = o.run(f, iters)
     with make(lbm, case) as lat:
-        assert "fuse=2" in lat.config
         lat.upload(f0)
         av_gpu = lat.run(iters, f64=True)
         assert_state_bit_exact(lat.download(), f)
         assert np.max(np.abs(av_gpu - av) / np.abs(av)) <= 1e-12
-        av2 = o.run(f, 5)
-        av_gpu2 = lat.run(5, f64=True)          # continue: 2 passes + 1 plain step
+        av2 = o.run(f, more)
+        av_gpu2 = lat.run(more, f64=True)       # continue from the canonical state: passes + plain steps
         assert_state_bit_exact(lat.download(), f)
         assert np.max(np.abs(av_gpu2 - av2) / np.abs(av2)) <= 1e-12
+        return lat.config
+
+
+@pytest.mark.parametrize("nx,ny", STREAM_SIZES)
+@pytest.mark.parametrize("iters", [2, 7, 40])
+def test_two_step_passes_bit_exact(lbm, nx, ny, iters, monkeypatch):
+    """temporal blocking through the TMA-fed shared-memory pipeline: same arithmetic per cell and step,
+    so still bit-identical to the oracle; odd counts end with one ordinary step"""
+    monkeypatch.setenv("LBM_FUSE", "2")
+    monkeypatch.setenv("LBM_CHUNK", "12")
+    case = cases.random_case(nx, ny, seed=nx + 3 * ny, walls=(ny > 8))
+    f0 = cases.perturbed_state(case, seed=nx)
+    cfg = _run_and_compare(lbm, case, f0, iters)
+    assert "fuse=2" in cfg and "stream=tma(S=2" in cfg
+
+
+@pytest.mark.parametrize("fuse,cfg,tile_h", [(3, None, None), (4, None, None), (2, 2, None), (2, 4, None),
+                                             (3, 6, None), (2, 0, 10), (3, 1, 8), (2, 5, None)])
+@pytest.mark.parametrize("nx,ny", [(512, 37), (1008, 64), (16384, 19)])
+def test_stream_kernel_shapes_bit_exact(lbm, fuse, cfg, tile_h, nx, ny, monkeypatch):
+    """every instantiated shape of the streaming kernel (steps per pass, warps per group, TMA stages),
+    small tile heights (many tiles per strip: the overlap rows between tiles are recomputed)"""
+    monkeypatch.setenv("LBM_FUSE", str(fuse))
+    monkeypatch.setenv("LBM_CHUNK", "12")
+    if cfg is not None:
+        monkeypatch.setenv("LBM_STREAM_CFG", str(cfg))
+    if tile_h is not None:
+        monkeypatch.setenv("LBM_TILE_H", str(tile_h))
+    case = cases.random_case(nx, ny, seed=nx + 5 * ny + fuse, walls=True)
+    f0 = cases.perturbed_state(case, seed=ny)
+    got = _run_and_compare(lbm, case, f0, 25, more=7)
+    assert "stream=tma(S=" in got
+
+
+@pytest.mark.parametrize("nx,ny", [(136, 40), (1000, 33), (248, 64), (512, 12), (64, 64)])
+def test_streaming_falls_back_to_the_one_step_kernel(lbm, nx, ny, monkeypatch):
+    """widths that are not a multiple of 16 (TMA row pitch), nx < 128, or fewer than 16 rows per slab"""
+    monkeypatch.setenv("LBM_FUSE", "2")
+    case = cases.random_case(nx, ny, seed=nx + ny, walls=True)
+    f0 = cases.perturbed_state(case, seed=nx)
+    assert "fuse=1" in _run_and_compare(lbm, case, f0, 9)
 
 
 def test_two_step_passes_shipped_case(lbm, monkeypatch):
@@ -411,17 +446,69 @@ def test_two_step_passes_shipped_case(lbm, monkeypatch):
         assert np.max(np.abs(av_gpu - av) / np.abs(av)) <= 1e-12
 
 
-@pytest.mark.parametrize("world", [2, 3, 8])
-def test_two_step_passes_one_process_per_gpu(lbm, world):
-    if _gpus(lbm) < world:
-        pytest.skip("needs %d GPUs" % world)
+def test_periodic_seam_without_walls(lbm, monkeypatch):
+    """no walls at y = 0 / ny-1: the flow crosses the periodic seam, so the ghost zones (depth 4, all nine
+    planes, obstacle and acceleration flags of the mirrored rows) carry real data every pass"""
+    for fuse in ("2", "3", "4"):
+        monkeypatch.setenv("LBM_FUSE", fuse)
+        case = cases.random_case(256, 48, seed=77, walls=False, fill=0.03)
+        f0 = cases.perturbed_state(case, seed=78, amp=0.1)
+        assert ("fuse=%s" % fuse) in _run_and_compare(lbm, case, f0, 36)
+
+
+def _torchrun(world, script_args, env, timeout=300):
     import sys
-    env = dict(os.environ, LBM_FUSE="2")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
-           os.path.join(cases.ROOT, "tools", "multirank_check.py"), "--nx", "512", "--ny", "100",
-           "--steps", "41"]
-    r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=300)
+           os.path.join(cases.ROOT, "tools", "multirank_check.py")] + script_args
+    return subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=timeout)
+
+
+@pytest.mark.parametrize("world,fuse,reduce", [(2, 2, "batched"), (3, 2, "batched"), (8, 2, "batched"),
+                                               (2, 3, "batched"), (4, 4, "batched"), (8, 3, "step"),
+                                               (2, 2, "step"), (4, 2, "step")])
+def test_stream_passes_one_process_per_gpu(lbm, world, fuse, reduce):
+    if _gpus(lbm) < world:
+        pytest.skip("needs %d GPUs" % world)
+    env = dict(os.environ, LBM_FUSE=str(fuse), LBM_CHUNK="12")
+    if reduce == "step":
+        env["LBM_REDUCE"] = "step"
+    r = _torchrun(world, ["--nx", "512", "--ny", "%d" % (50 * world + 3), "--steps", "41"], env)
     print(r.stdout[-600:])
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    assert "-> OK" in r.stdout and "fuse=2" in r.stdout
+    assert "-> OK" in r.stdout and ("fuse=%d" % fuse) in r.stdout
+    if reduce == "step":
+        assert "in-kernel-allreduce-per-step" in r.stdout
+
+
+@pytest.mark.parametrize("ngpus,fuse", [(2, 2), (4, 3), (8, 2)])
+def test_stream_passes_one_process_row_slabs(lbm, ngpus, fuse, monkeypatch):
+    """lbm_create(ngpus=N) -- the mode d2q9-bgk.exe uses with LBM_GPUS=N -- with the streaming kernel:
+    same in-kernel ring as the one-process-per-GPU mode, peer pointers by cudaDeviceEnablePeerAccess"""
+    if _gpus(lbm) < ngpus:
+        pytest.skip("needs %d GPUs" % ngpus)
+    monkeypatch.setenv("LBM_FUSE", str(fuse))
+    monkeypatch.setenv("LBM_CHUNK", "12")
+    case = cases.random_case(512, 40 * ngpus + 5, seed=21, walls=True)
+    f0 = cases.perturbed_state(case, seed=21)
+    o = Oracle("f32b200", case)
+    f = f0.copy()
+    av = o.run(f, 31)
+    with make(lbm, case, ngpus=ngpus) as lat:
+        assert "slabs=%d" % ngpus in lat.config and ("fuse=%d" % fuse) in lat.config
+        lat.upload(f0)
+        av_gpu = lat.run(31, f64=True)
+        assert_state_bit_exact(lat.download(), f)
+        assert np.max(np.abs(av_gpu - av) / np.abs(av)) <= 1e-12
+
+
+def test_ring_timeout_is_an_error_not_a_hang(lbm):
+    """negative test: rank 1 never publishes its progress (LBM_TEST_RING_STALL=1); its neighbours give up
+    after the bounded spin and every rank's lbm_run returns the time-out error"""
+    if _gpus(lbm) < 2:
+        pytest.skip("needs 2 GPUs")
+    env = dict(os.environ, LBM_FUSE="2", LBM_TEST_RING_STALL="1")
+    r = _torchrun(2, ["--nx", "512", "--ny", "100", "--steps", "8", "--expect-timeout"], env, timeout=240)
+    print(r.stdout[-600:])
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "timed out waiting for a neighbour GPU" in r.stdout and "-> OK" in r.stdout

@@ -30,6 +30,8 @@ def main():
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--seed", type=int, default=11)
     ap.add_argument("--channel", action="store_true", help="synthetic channel instead of random obstacles")
+    ap.add_argument("--expect-timeout", action="store_true",
+                    help="negative test (LBM_TEST_RING_STALL): every rank's run must fail with the time-out error")
     a = ap.parse_args()
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
@@ -52,6 +54,23 @@ def main():
     assert (lat.y0, lat.rows) == (y0, rows)
     assert lat.tot_cells == case.tot_cells, (lat.tot_cells, case.tot_cells)
     lat.upload(np.ascontiguousarray(f0[:, y0 * nx:(y0 + rows) * nx]))
+    if a.expect_timeout:
+        try:
+            lat.run(a.steps, f64=True)
+            msg = "no error"
+        except lbm.LbmError as e:
+            msg = str(e)
+        lat.close()
+        msgs = [None] * world if rank == 0 else None
+        dist.gather_object(msg, msgs, dst=0)
+        ok = True
+        if rank == 0:
+            ok = all("timed out waiting for a neighbour GPU" in m for m in msgs)
+            print("multirank_check: expected time-out: %s -> %s" % (msgs, "OK" if ok else "FAIL"), flush=True)
+        flag = [ok]
+        dist.broadcast_object_list(flag, src=0)
+        dist.destroy_process_group()
+        return 0 if flag[0] else 1
     av1 = lat.run(a.steps, f64=True)
     av2 = lat.run(5, f64=True)                     # a second run continues from the canonical state
     av3 = np.array([lat.step() for _ in range(3)])
