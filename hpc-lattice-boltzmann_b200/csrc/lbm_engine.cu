@@ -581,6 +581,7 @@ int launch_stream(lbm_lattice* h, Slab& s, int cur, int fuse_last, int slot, lon
   a.ps_hi = s.hi_ps;
   a.partials = s.partials + (long long)slot * s.np;
   a.np = s.np;
+  a.debug = env_int("LBM_STREAM_DEBUG", 0);
   if (h->ring) {
     a.ring_in = s.sync;
     a.ring_out_lo = h->stall_test ? s.sync + 8 : s.ring_out_lo;
@@ -892,7 +893,7 @@ int make_tensor_maps(const lbm_lattice* h, Slab& s)
   {
     const cuuint64_t dims[2] = {nx, nrows};
     const cuuint64_t strides[1] = {nx};
-    const cuuint32_t box[2] = {(cuuint32_t)lbm::S_TILE_W, (cuuint32_t)c.nw};
+    const cuuint32_t box[2] = {(cuuint32_t)lbm::S_FLAG_BOX, (cuuint32_t)c.nw};
     const cuuint32_t es[2] = {1, 1};
     const CUresult r = enc(&s.tm_flags, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, s.flags, dims, strides, box, es,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
