@@ -184,7 +184,7 @@ const StreamCfg STREAM_CFGS[] = {
     {2, 8, 3, 1},   // 2: 544 threads, 194 KB
     {4, 4, 2, 1},   // 3: 544 threads, 176 KB
     {2, 3, 2, 3},   // 4: 224 threads, 65 KB: three blocks per SM
-    {1, 4, 4, 3},   // 5: one step per pass (TMA flavour of the one-step kernel), 74 KB
+    {2, 4, 2, 2},   // 5: as 0 with two TMA stages
     {3, 4, 2, 1},   // 6: 416 threads, 130 KB
 };
 constexpr int N_STREAM_CFGS = sizeof(STREAM_CFGS) / sizeof(STREAM_CFGS[0]);
@@ -544,7 +544,7 @@ cudaError_t configure_stream_t()
     case 2: return CALL(2, 8, 3, 1);                   \
     case 3: return CALL(4, 4, 2, 1);                   \
     case 4: return CALL(2, 3, 2, 3);                   \
-    case 5: return CALL(1, 4, 4, 3);                   \
+    case 5: return CALL(2, 4, 2, 2);                   \
     case 6: return CALL(3, 4, 2, 1);                   \
     default: return CALL(2, 4, 3, 2);                  \
   }
