@@ -581,7 +581,6 @@ int launch_stream(lbm_lattice* h, Slab& s, int cur, int fuse_last, int slot, lon
   a.ps_hi = s.hi_ps;
   a.partials = s.partials + (long long)slot * s.np;
   a.np = s.np;
-  a.debug = env_int("LBM_STREAM_DEBUG", 0);
   if (h->ring) {
     a.ring_in = s.sync;
     a.ring_out_lo = h->stall_test ? s.sync + 8 : s.ring_out_lo;
