@@ -79,3 +79,36 @@ def test_host_program_fails_loudly_without_gpu(lbm, tmp_path):
     r = run_exe(lbm, [pf, of], tmp_path)
     assert r.returncode == 1 and "no CUDA device" in r.stderr
     assert not (tmp_path / "av_vels.dat").exists()
+
+
+def test_parallel_obstacle_parser_equals_the_reference_loop(lbm, tmp_path):
+    """the mmap + OpenMP parser of host/d2q9-bgk.c against the reference's fscanf loop
+    (d2q9-bgk.c:615-628, kept behind LBM_SERIAL_PARSE=1): same obstacle map for well-formed files
+    (with duplicates, blank lines, CRLF, no final newline) and, through the fallback, for files the
+    fast scanner declines (three values spread over several lines)"""
+    case = cases.random_case(300, 200, seed=4, fill=0.3)
+    pf, of = case.write(str(tmp_path))
+    body = open(of).read()
+    variants = {
+        "plain": body,
+        "dups_blank_crlf": body + body[:4000] + "\n\n" + "5 7 1\r\n" + "9   11\t1  \n" + "12 13 1",
+        "spread": "1 2\n1\n" + body,            # fscanf semantics: whitespace includes newlines
+        "empty": "",
+    }
+    for name, text in variants.items():
+        path = tmp_path / (name + ".dat")
+        path.write_text(text)
+        outs = []
+        for serial in (False, True):
+            env = dict(os.environ, LBM_PARSE_ONLY="1")
+            if serial:
+                env["LBM_SERIAL_PARSE"] = "1"
+            r = subprocess.run([lbm.EXE_PATH, pf, str(path)], cwd=tmp_path, capture_output=True, text=True, env=env)
+            assert r.returncode == 0, (name, r.stderr)
+            outs.append(r.stdout)
+        assert outs[0] == outs[1] and outs[0].startswith("parsed: 300 x 200"), (name, outs)
+    # and errors keep the reference's diagnostics (first offending entry, found by the fallback)
+    (tmp_path / "bad.dat").write_text(body + "300 1 1\n")
+    r = subprocess.run([lbm.EXE_PATH, pf, "bad.dat"], cwd=tmp_path, capture_output=True, text=True,
+                       env=dict(os.environ, LBM_PARSE_ONLY="1"))
+    assert r.returncode == 1 and "obstacle x-coord out of range" in r.stderr
