@@ -6,14 +6,26 @@
 One "step" = one lattice timestep (accelerate + propagate + rebound + collision + av_velocity)
 over the whole grid.  The default workload is BASELINE.json's synthetic 16384x16384 channel
 (18 GiB of state: larger than L2 by construction, so no cache flush is needed between steps);
-with N GPUs the same grid is row-slabbed over the ranks ("scaling": "strong").  The reference's
-shipped 1024x1024 case is timed as well and reported under "extra" (its 75 MB working set is
-L2-resident on a B200 -- stated there).
+with N GPUs the same grid is row-slabbed over the ranks ("scaling": "strong").
 
-Keys beyond the base contract: "roofline" (HBM, 72 algorithmic bytes per lattice update, against
-MEASURED_PEAKS.json), "cpu_baseline" (the unmodified reference, oracle/_ref, on the host cores, on
-a bounded square crop of the same channel), "e2e" (host planes -> lbm_upload -> lbm_run ->
-lbm_download -> host, wall clock, the reference's own tic/toc region d2q9-bgk.c:155-275).
+What one JSON line holds (beyond the base contract):
+  value / ms_per_step   MEDIAN of `repeats` back-to-back timed regions of exactly K steps each (CUDA
+                        events on the engine's stream, max over ranks); min / max / all samples in
+                        "timing"
+  roofline              HBM; `achieved`, `frac` = 72 algorithmic bytes per update against
+                        MEASURED_PEAKS.json -- may exceed 1 because the streaming kernel advances S
+                        timesteps per pass; `achieved_dram`, `frac_dram` = DRAM bytes the kernel really
+                        moves (ncu, profiles/traffic.json) / time / peak: the number to optimise
+  roofline_1024         the north-star's 1024x1024 case (L2-resident): HBM roofline fraction and the
+                        fraction of an L2 copy bandwidth measured in this run
+  e2e                   host planes -> lbm_upload -> lbm_run(K) -> lbm_download -> host, wall clock (the
+                        reference's own tic/toc region, d2q9-bgk.c:155-275)
+  config.state_digest   64-bit sum and xor of the uint32 bit patterns of the state after the e2e leg,
+  config.av_vels_digest combined over the ranks; identical at N = 1, 2, 4, 8 when every GPU count
+                        computes the same thing (the N = 1 path is pinned to the oracle by the tests)
+  cpu_baseline          the unmodified reference (oracle/_ref) on the host cores, bounded square crop
+  extra                 per-step in-kernel allreduce variant (N > 1), BASELINE.json's config 5
+                        (8192x65536), d2q9-bgk.exe on the same workload with LBM_GPUS=N
 
 `--impl reference` times the reference's CPU implementation of the path instead (rank 0 only).
 This file is one of the three places allowed to touch oracle/ -- only as the timed CPU baseline.
@@ -22,6 +34,7 @@ import argparse
 import importlib
 import json
 import os
+import re
 import shutil
 import statistics
 import subprocess
@@ -38,6 +51,7 @@ from tools import cases  # noqa: E402
 
 BYTES_PER_UPDATE = 72.0          # 9 float32 loads + 9 float32 stores
 FALLBACK_HBM_GBS = 6650.0        # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+DENSITY, ACCEL, OMEGA = 0.1, 0.005, 1.85
 
 
 def hbm_peak():
@@ -101,11 +115,14 @@ def dist_env():
 # ----------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the UNMODIFIED reference (oracle/_ref) on the host cores
 # ----------------------------------------------------------------------------------------------
-def time_reference_cpu(nx_full, ny_full, steps, warmup, crop=2048, budget_s=25.0):
+def time_reference_cpu(nx_full, ny_full, steps, warmup, crop=8192, budget_s=25.0):
     """Times the reference's own timestep() (d2q9-bgk.c:294-298 -> kernels.cl, compiled unmodified
-    against the host-memory OpenCL shim; OpenMP over the NDRange in the shim) on a square crop of
-    the workload: the reference's kernel indexing only works for nx == ny (quirk Q1) and one step
-    of the full grid would take ~10 s of CPU.  Returns a dict for "cpu_baseline"."""
+    against the host-memory OpenMP shim) on a square crop of the workload: the reference's kernel
+    indexing only works for nx == ny (quirk Q1), its per-step host sum keeps an nx*ny-float array on
+    the stack (d2q9-bgk.c:349; the shim's helper thread gives it one) and, with the host-memory
+    "device" buffers, it holds the state four times over: 8192^2 (10 GiB, ~0.3 s per step on 16 cores)
+    is the largest power-of-two square that fits a 1-GPU box's host memory next to this benchmark's own
+    pinned planes.  MLUPS is size-normalised.  Returns a dict for "cpu_baseline"."""
     # every host thread this process may use; torch.distributed.run exports OMP_NUM_THREADS=1, and
     # libgomp reads the variable once, when the checker library pulls it in (not loaded before here)
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
@@ -150,9 +167,9 @@ def run_reference_arm(a, nx, ny, emit):
     rank, world, _ = dist_env()
     if rank != 0:
         return 0
-    cb = time_reference_cpu(nx, ny, a.steps, a.warmup)
+    cb = time_reference_cpu(nx, ny, a.steps, min(a.warmup, 2))
     line = {"impl": "reference", "metric": "MLUPS", "value": cb["value"], "unit": "MLUPS",
-            "n_gpus": a.gpus, "steps": cb["steps"], "warmup": max(1, a.warmup),
+            "n_gpus": a.gpus, "steps": cb["steps"], "warmup": max(1, min(a.warmup, 2)),
             "ms_per_step": cb["ms_per_step_sample"], "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "d2q9-bgk %dx%d synthetic channel, seed 42" % (nx, ny),
@@ -168,16 +185,171 @@ def run_reference_arm(a, nx, ny, emit):
 # ----------------------------------------------------------------------------------------------
 # own arm
 # ----------------------------------------------------------------------------------------------
-def time_case_on_gpu(lbm, case_name, steps, warmup):
-    """extra: one of the shipped cases on one GPU, device-resident (init on device)"""
-    case = cases.shipped(case_name)
+class Ranks:
+    """torch.distributed as plumbing: barrier, max / sum over ranks, the ncclUniqueId"""
+
+    def __init__(self, lbm):
+        self.rank, self.world, self.local = dist_env()
+        self.dist = None
+        self.lbm = lbm
+        if self.world > 1:
+            import torch
+            import torch.distributed as dist
+            self.torch, self.dist = torch, dist
+            torch.cuda.set_device(self.local)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+
+    def unique_id(self):
+        if self.dist is None:
+            return None
+        t = self.torch.zeros(128, dtype=self.torch.uint8, device="cuda")
+        if self.rank == 0:
+            t.copy_(self.torch.frombuffer(bytearray(self.lbm.comm_unique_id()), dtype=self.torch.uint8))
+        self.dist.broadcast(t, 0)
+        return bytes(t.cpu().numpy().tobytes())
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+
+    def reduce(self, x, op="max"):
+        if self.dist is None:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX if op == "max" else self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def gather_u64(self, values):
+        """all ranks' uint64 tuples, in rank order (bit patterns travel as int64)"""
+        v = np.asarray(values, dtype=np.uint64)
+        if self.dist is None:
+            return [v]
+        mine = self.torch.from_numpy(v.view(np.int64).copy()).cuda()
+        out = [self.torch.empty_like(mine) for _ in range(self.world)]
+        self.dist.all_gather(out, mine)
+        return [o.cpu().numpy().view(np.uint64) for o in out]
+
+    def close(self):
+        if self.dist is not None:
+            self.dist.destroy_process_group()
+
+
+def make_lattice(lbm, R, nx, ny, uid):
+    y0, rows = lbm.slab_rows(ny, R.world, R.rank)
+    ob = cases.channel(nx, ny, rows=(y0, rows))
+    if R.world == 1:
+        lat = lbm.Lattice(nx, ny, DENSITY, ACCEL, OMEGA, ob)
+    else:
+        lat = lbm.Lattice(nx, ny, DENSITY, ACCEL, OMEGA, ob, rank=R.rank, world=R.world, device=R.local,
+                          unique_id=uid)
+    return lat, rows
+
+
+def timed_runs(lat, R, steps, warmup, repeats):
+    """`repeats` timed regions of exactly `steps` timesteps each; every region is bracketed by a
+    barrier and timed by CUDA events on the engine's stream (lbm_run returns after the last step);
+    the per-region time is the max over ranks"""
+    lat.init_equilibrium()
+    lat.run(warmup)
+    samples, launches = [], 0
+    for _ in range(repeats):
+        R.barrier()
+        lat.run(steps)
+        samples.append(R.reduce(lat.last_run_ms))
+        launches = lat.last_run_launches
+    R.barrier()
+    return samples, launches
+
+
+def state_digest(planes):
+    """64-bit wrap-around sum and xor of the uint32 bit patterns of a rank's planes"""
+    u = planes.view(np.uint32)
+    return int(u.sum(dtype=np.uint64)), int(np.bitwise_xor.reduce(u.reshape(-1)))
+
+
+def l2_copy_bandwidth():
+    """device-to-device copy of two 16 MiB buffers (both L2-resident on a B200), GB/s read+write:
+    the L2 denominator for the 1024^2 case.  torch is plumbing here (a memcpy and two events)."""
+    try:
+        import torch
+        n = 16 << 20
+        a = torch.empty(n, dtype=torch.uint8, device="cuda")
+        b = torch.empty(n, dtype=torch.uint8, device="cuda")
+        for _ in range(20):
+            b.copy_(a)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        best = None
+        for _ in range(5):
+            e0.record()
+            for _ in range(200):
+                b.copy_(a)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 200
+            best = ms if best is None else min(best, ms)
+        return 2.0 * n / (best / 1e3) / 1e9
+    except Exception:
+        return None
+
+
+def time_shipped_1024(lbm, peak):
+    """the reference's shipped 1024x1024 case, all 20000 steps, state initialised on the device"""
+    case = cases.shipped("1024x1024")
     with lbm.Lattice(case.nx, case.ny, case.density, case.accel, case.omega, case.obstacles) as lat:
         lat.init_equilibrium()
-        lat.run(warmup)
-        lat.run(steps)
-        ms = lat.last_run_ms
-        return {"mlups": case.cells * steps / (ms / 1e3) / 1e6, "ms_per_step": ms / steps,
-                "steps": steps, "config": lat.config}
+        lat.run(2000)
+        best = None
+        for _ in range(3):
+            lat.run(20000)
+            best = lat.last_run_ms if best is None else min(best, lat.last_run_ms)
+        cfg = lat.config
+    mlups = case.cells * 20000 / (best / 1e3) / 1e6
+    achieved = mlups * 1e6 * BYTES_PER_UPDATE / 1e9
+    l2 = l2_copy_bandwidth()
+    return {"workload": "reference's shipped 1024x1024 case, all 20000 steps, best of 3",
+            "value": mlups, "unit": "MLUPS", "ms_per_step": best / 20000, "bound": "l2 (75.5 MB of state, "
+            "double-buffered, lives in the 126 MB L2; DRAM sees ~0.1 MB per step, profiles/r1_ncu_warm_dram_1024x1024.csv)",
+            "achieved": achieved, "unit_bw": "GB/s", "peak_hbm": peak, "frac": achieved / peak,
+            "frac_hbm": achieved / peak, "peak_l2": l2, "frac_l2": (achieved / l2) if l2 else None,
+            "peak_l2_source": "device-to-device copy of 2 x 16 MiB measured in this run (read + write bytes)",
+            "kernel": "lbm_step_kernel<4,128>", "algorithmic_bytes_per_update": BYTES_PER_UPDATE,
+            "north_star_target_frac_hbm": 0.75, "engine": cfg}
+
+
+def run_exe(lbm, nx, ny, steps, ngpus):
+    """d2q9-bgk.exe <paramfile> <obstaclefile> on the same synthetic workload with LBM_GPUS=ngpus:
+    the C product end to end (text parse, device init, run, 4-plane read-back; final_state.dat is
+    not written for a 16 GiB text file)"""
+    tmp = tempfile.mkdtemp(prefix="lbm_exe_")
+    try:
+        case = cases.channel(nx, ny)
+        t0 = time.perf_counter()
+        pf, of = case.write(tmp, iters=steps)
+        write_s = time.perf_counter() - t0
+        env = dict(os.environ, LBM_GPUS=str(ngpus), LBM_SKIP_FINAL_STATE="1")
+        for k in ("LBM_FUSE", "LBM_REDUCE"):
+            env.pop(k, None)
+        cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        env["OMP_NUM_THREADS"] = str(cores)
+        t0 = time.perf_counter()
+        r = subprocess.run([lbm.EXE_PATH, pf, of], cwd=tmp, capture_output=True, text=True, env=env, timeout=900)
+        wall = time.perf_counter() - t0
+        if r.returncode != 0:
+            return {"error": (r.stderr or r.stdout)[-400:]}
+        out = {"gpus": ngpus, "steps": steps, "process_wall_s": wall, "case_files_written_s": write_s}
+        for key, pat in (("elapsed_s", r"Elapsed time:\s+([0-9.]+)"), ("loop_s", r"GPU timestep loop:\s+([0-9.]+)"),
+                         ("mlups_loop", r"MLUPS \(timestep loop\):\s+([0-9.]+)"),
+                         ("mlups_elapsed", r"MLUPS \(elapsed time\):\s+([0-9.]+)"),
+                         ("parse_s", r"Input parse:\s+([0-9.]+)")):
+            m = re.search(pat, r.stdout)
+            if m:
+                out[key] = float(m.group(1))
+        m = re.search(r"GPUs:\s+\d+ \((.*)\)", r.stdout)
+        if m:
+            out["engine"] = m.group(1)
+        return out
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
 
 
 def main():
@@ -185,12 +357,14 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--repeats", type=int, default=25, help="timed regions of --steps steps each (median reported)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="16384x16384")
-    ap.add_argument("--no-extra", action="store_true", help="skip the 1024x1024 / cpu_baseline legs")
+    ap.add_argument("--no-extra", action="store_true", help="headline + e2e only")
     a = ap.parse_args()
     nx, ny = (int(v) for v in a.workload.lower().split("x"))
     a.warmup = max(3, a.warmup)
+    a.repeats = max(1, a.repeats)
     # stdout carries exactly one JSON line: anything a library prints there (NCCL's version
     # banner, the reference's device list) is sent to stderr instead
     sys.stdout.flush()
@@ -215,107 +389,146 @@ def main():
 
     lbm = importlib.import_module("hpc-lattice-boltzmann_b200")
     lbm.load()                                    # loud failure if the CUDA library is missing
-
-    dist = None
-    uid = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        uid_t = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            uid_t.copy_(torch.frombuffer(bytearray(lbm.comm_unique_id()), dtype=torch.uint8))
-        dist.broadcast(uid_t, 0)
-        uid = bytes(uid_t.cpu().numpy().tobytes())
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-
-    def max_over_ranks(x):
-        if dist is None:
-            return x
-        import torch
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    y0, rows = lbm.slab_rows(ny, world, rank)
-    ob = cases.channel(nx, ny, rows=(y0, rows))
-    density, accel, omega = 0.1, 0.005, 1.85
-    if world == 1:
-        lat = lbm.Lattice(nx, ny, density, accel, omega, ob)
-    else:
-        lat = lbm.Lattice(nx, ny, density, accel, omega, ob, rank=rank, world=world, device=local,
-                          unique_id=uid)
-    del ob
+    R = Ranks(lbm)
+    uid = R.unique_id()
 
     # ---- device-resident throughput ("value") ---------------------------------------------
-    lat.init_equilibrium()
-    lat.run(a.warmup)
-    barrier()
+    lat, rows = make_lattice(lbm, R, nx, ny, uid)
     sampler = ClockSampler(local) if rank == 0 else None
-    lat.run(a.steps)                              # synchronous: returns after the last step
-    ms = max_over_ranks(lat.last_run_ms)          # CUDA events on the engine's own stream
-    barrier()
+    samples, launches = timed_runs(lat, R, a.steps, a.warmup, a.repeats)
     clocks = sampler.stop() if sampler else None
-    launches = lat.last_run_launches
+    ms = statistics.median(samples)
     mlups = nx * ny * a.steps / (ms / 1e3) / 1e6
 
     # ---- end to end through the C ABI with host buffers ("e2e") ----------------------------
     cells_local = rows * nx
     pinned = lbm.PinnedPlanes(cells_local)
-    d = np.float32(density)
+    d = np.float32(DENSITY)
     pinned.array[0] = np.float32(np.float64(d) * 4.0 / 9.0)
     pinned.array[1:5] = np.float32(np.float64(d) / 9.0)
     pinned.array[5:9] = np.float32(np.float64(d) / 36.0)
-    barrier()
+    R.barrier()
     t0 = time.perf_counter()
     lat.upload(pinned.array)
     av = lat.run(a.steps)
     lat.download(pinned.array)
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    barrier()
+    e2e_s = R.reduce(time.perf_counter() - t0)
+    R.barrier()
     e2e_mlups = nx * ny * a.steps / e2e_s / 1e6
     finite = bool(np.all(np.isfinite(av)) and np.all(av > 0))
+    # digests of what the e2e leg computed: the slabs partition the lattice, so the wrap-around sum
+    # and the xor over all ranks' slabs do not depend on how many ranks there are
+    s_sum, s_xor = state_digest(pinned.array)
+    parts = R.gather_u64([s_sum, s_xor])
+    tot_sum = int(np.sum(np.array([p[0] for p in parts], dtype=np.uint64), dtype=np.uint64))
+    tot_xor = int(np.bitwise_xor.reduce(np.array([p[1] for p in parts], dtype=np.uint64)))
+    av32 = np.ascontiguousarray(av, dtype=np.float32).view(np.uint32)
+    av_digest = "%016x" % (int(av32.sum(dtype=np.uint64)) ^ (int(np.bitwise_xor.reduce(av32)) << 32))
     pinned.free()
     config_string = lat.config
     lat.close()
 
+    # ---- extras --------------------------------------------------------------------------------
+    extra = {}
+    m = re.search(r"fuse=(\d+)", config_string)
+    S = int(m.group(1)) if m else 1
+    if not a.no_extra:
+        if world > 1:
+            # the north-star's per-step allreduce of the speed sum, done by the step kernel itself
+            os.environ["LBM_REDUCE"] = "step"
+            try:
+                lat2, _ = make_lattice(lbm, R, nx, ny, uid)
+                s2, _l = timed_runs(lat2, R, a.steps, a.warmup, min(a.repeats, 7))
+                av2 = lat2.run(8)
+                cfg2 = lat2.config
+                lat2.close()
+                ms2 = statistics.median(s2)
+                extra["allreduce_per_step"] = {
+                    "value": nx * ny * a.steps / (ms2 / 1e3) / 1e6, "unit": "MLUPS", "ms_per_step": ms2 / a.steps,
+                    "penalty_vs_batched_pct": 100.0 * (ms2 / ms - 1.0), "repeats": len(s2),
+                    "results_finite": bool(np.all(np.isfinite(av2))), "engine": cfg2,
+                    "what": "LBM_REDUCE=step: the last block of every launch adds up the launch's per-block "
+                            "speed sums and stores the slab total of each timestep into every rank's table "
+                            "over NVLink; no collective launch"}
+            finally:
+                del os.environ["LBM_REDUCE"]
+        # BASELINE.json configs[4]: the 8192 x 65536 long channel (nx = 8192, ny = 65536: the reference's
+        # <nx>x<ny> naming), 36 GiB of state in total
+        try:
+            lx, ly = 8192, 65536
+            lat5, _ = make_lattice(lbm, R, lx, ly, uid)
+            s5, _l = timed_runs(lat5, R, 100, 10, 5)
+            cfg5 = lat5.config
+            lat5.close()
+            ms5 = statistics.median(s5)
+            v5 = lx * ly * 100 / (ms5 / 1e3) / 1e6
+            peak5, _ = hbm_peak()
+            extra["8192x65536"] = {"value": v5, "unit": "MLUPS", "ms_per_step": ms5 / 100, "steps": 100, "repeats": 5,
+                                   "per_gpu_frac": v5 * 1e6 * BYTES_PER_UPDATE / 1e9 / world / peak5,
+                                   "engine": cfg5, "n_gpus": world}
+        except Exception as e:      # e.g. not enough memory on a small box: say so, keep the headline
+            extra["8192x65536"] = {"error": str(e)[:300]}
+        R.barrier()
+        if rank == 0:
+            # the C product on the same workload (all N GPUs driven by ONE host thread of one process);
+            # the other ranks idle at the barrier below
+            extra["exe"] = run_exe(lbm, nx, ny, a.steps, world)
+        R.barrier()
+
     if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
+        R.close()
         return 0
 
     peak, peak_src = hbm_peak()
     achieved = BYTES_PER_UPDATE * nx * ny * a.steps / (ms / 1e3) / 1e9 / world   # GB/s per GPU
-    fused = "fuse=2" in config_string
-    kernel = "lbm_fused2_kernel" if fused else "lbm_step_kernel"
-    steps_per_launch = 2 if fused else 1
-    roof_note = ("achieved = 72 algorithmic bytes x lattice updates / CUDA-event time of the timestep loop "
-                 "(step kernels are >= 97.9 % of it, profiles/r1_launches_bench_16384.csv)")
-    if fused:
-        roof_note += ("; the dominant kernel advances TWO timesteps per launch through shared-memory "
-                      "tiles, so its measured DRAM traffic (`traffic`, per launch) is about half of the "
-                      "algorithmic bytes and the fraction can exceed 1 -- every timestep is computed, "
-                      "bit-identically to the one-step kernel (tests/test_gpu_parity.py)")
+    streaming = S > 1
+    kernel = "lbm_stream_kernel" if streaming else "lbm_step_kernel"
+    traffic, traffic_src = None, None
+    traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.isfile(traffic_file):
+        try:
+            t = json.load(open(traffic_file))
+            key = "S=%d" % S
+            bpu = t["dram_bytes_per_update"][kernel].get(key)
+            traffic_src = t["source"]
+            if bpu:
+                traffic = bpu * S * nx * ny / world      # per launch and GPU
+        except Exception:
+            pass
+    achieved_dram = (traffic / S) * a.steps / (ms / 1e3) / 1e9 if traffic else None
     line = {
         "metric": "MLUPS", "value": mlups, "unit": "MLUPS", "n_gpus": world, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "timing": {"repeats": len(samples), "statistic": "median of the timed regions (each exactly `steps` steps)",
+                   "ms_per_step_min": min(samples) / a.steps, "ms_per_step_max": max(samples) / a.steps,
+                   "value_min": nx * ny * a.steps / (max(samples) / 1e3) / 1e6,
+                   "value_max": nx * ny * a.steps / (min(samples) / 1e3) / 1e6,
+                   "region_ms": [round(s, 4) for s in samples]},
         "config": {"workload": "d2q9-bgk %dx%d synthetic channel (walls y=0,ny-1; seed-42 8x8 "
                                "obstacle blocks), density 0.1 accel 0.005 omega 1.85" % (nx, ny),
                    "parallelism": "row slabs x%d" % world, "engine": config_string,
                    "l2": "state is %.1f GiB per GPU, far above the 126 MB L2: no flush needed"
                          % (18 * 4 * nx * ny / world / 2 ** 30),
-                   "results_finite": finite},
+                   "results_finite": finite,
+                   "state_digest": "sum=%016x xor=%08x" % (tot_sum, tot_xor),
+                   "av_vels_digest": av_digest,
+                   "digest_of": "state / float32 av_vels after the e2e leg (%d steps from the initial equilibrium); "
+                                "the same at every GPU count" % a.steps},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                     "kernel": kernel, "timesteps_per_launch": steps_per_launch,
+                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "kernel": kernel, "timesteps_per_launch": S,
                      "algorithmic_bytes_per_update": BYTES_PER_UPDATE,
-                     "algorithmic_bytes_per_launch": BYTES_PER_UPDATE * nx * ny / world * steps_per_launch,
-                     "per_gpu": True, "note": roof_note},
+                     "algorithmic_bytes_per_update_effective": BYTES_PER_UPDATE / S,
+                     "algorithmic_bytes_per_launch": BYTES_PER_UPDATE * nx * ny / world * S,
+                     "achieved_dram": achieved_dram, "frac_dram": (achieved_dram / peak) if achieved_dram else None,
+                     "traffic_source": traffic_src, "per_gpu": True,
+                     "note": "achieved / frac use the contract's 72 algorithmic bytes per update; the streaming "
+                             "kernel advances %d timesteps per pass through shared memory, so it moves about "
+                             "72 / %d bytes per update and `frac` can exceed 1 -- `achieved_dram` / `frac_dram` "
+                             "(measured DRAM bytes per launch / launch time / peak) is the kernel's real HBM "
+                             "utilisation; every timestep is computed, bit-identically to the one-step kernel "
+                             "(tests/test_gpu_parity.py)" % (S, S)},
         "e2e": {"value": e2e_mlups, "unit": "MLUPS",
                 "h2d_bytes_per_step": 36.0 * nx * ny / a.steps,
                 "d2h_bytes_per_step": (36.0 * nx * ny + 4.0 * a.steps) / a.steps,
@@ -325,26 +538,13 @@ def main():
         "gpu_launches": launches,
         "clocks": clocks,
     }
-    traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.isfile(traffic_file):
-        try:
-            t = json.load(open(traffic_file)).get(a.workload)
-            if isinstance(t, dict):
-                t = t.get(kernel)
-            line["roofline"]["traffic"] = t / world if t and world > 1 else t
-        except Exception:
-            pass
-    if world == 1 and not a.no_extra:
-        line["cpu_baseline"] = time_reference_cpu(nx, ny, a.steps, 1)
-        ex = time_case_on_gpu(lbm, "1024x1024", 20000, 2000)
-        ex["roofline_frac"] = ex["mlups"] * 1e6 * BYTES_PER_UPDATE / 1e9 / peak
-        ex["note"] = ("reference's shipped 1024x1024 case, all 20000 steps, state initialised on the "
-                      "device; 75.5 MB double-buffered working set is L2-resident on B200, so the "
-                      "fraction is against the HBM roofline but served largely from L2")
-        line["extra"] = {"1024x1024": ex}
+    if not a.no_extra:
+        if world == 1:
+            line["cpu_baseline"] = time_reference_cpu(nx, ny, a.steps, 1)
+            line["roofline_1024"] = time_shipped_1024(lbm, peak)
+        line["extra"] = extra
     emit(line)
-    if dist is not None:
-        dist.destroy_process_group()
+    R.close()
     return 0
 
 

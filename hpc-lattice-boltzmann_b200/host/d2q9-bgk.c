@@ -258,8 +258,10 @@ int main(int argc, char* argv[])
   }
 
   run_config cfg;
+  const double parse_tic = wall_seconds();
   read_param_file(argv[1], &cfg);
   int* blocked_map = read_obstacle_file(argv[2], &cfg);
+  const double parse_toc = wall_seconds();
   if (env_flag("LBM_PARSE_ONLY", 0)) {
     unsigned long long blocked = 0, sum = 1469598103934665603ULL;
     for (size_t i = 0; i < (size_t)cfg.nx * cfg.ny; i++) {
@@ -313,6 +315,7 @@ int main(int argc, char* argv[])
   printf("Elapsed system CPU time:\t%.6lf (s)\n", systim);
   /* additions (after the reference's block, so scripts that parse it keep working) */
   const double lups = (double)cells * cfg.max_iters;
+  printf("Input parse:\t\t\t%.6lf (s)\n", parse_toc - parse_tic);
   printf("GPU timestep loop:\t\t%.6lf (s)\n", loop_ms / 1e3);
   if (loop_ms > 0.0) {
     const double mlups = lups / (loop_ms / 1e3) / 1e6;
