@@ -198,6 +198,7 @@ class Ranks:
             self.torch, self.dist = torch, dist
             torch.cuda.set_device(self.local)
             dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+            self.cpu_group = dist.new_group(backend="gloo")
 
     def unique_id(self):
         if self.dist is None:
@@ -211,6 +212,12 @@ class Ranks:
     def barrier(self):
         if self.dist is not None:
             self.dist.barrier()
+
+    def cpu_barrier(self):
+        """a barrier that leaves the GPUs alone (an NCCL barrier parks a spinning kernel on every GPU
+        that waits, which would time-slice against another process using that GPU)"""
+        if self.dist is not None:
+            self.dist.barrier(group=self.cpu_group)
 
     def reduce(self, x, op="max"):
         if self.dist is None:
@@ -234,7 +241,8 @@ class Ranks:
             self.dist.destroy_process_group()
 
 
-def make_lattice(lbm, R, nx, ny, uid):
+def make_lattice(lbm, R, nx, ny):
+    uid = R.unique_id()          # one ncclUniqueId per communicator
     y0, rows = lbm.slab_rows(ny, R.world, R.rank)
     ob = cases.channel(nx, ny, rows=(y0, rows))
     if R.world == 1:
@@ -267,31 +275,6 @@ def state_digest(planes):
     return int(u.sum(dtype=np.uint64)), int(np.bitwise_xor.reduce(u.reshape(-1)))
 
 
-def l2_copy_bandwidth():
-    """device-to-device copy of two 16 MiB buffers (both L2-resident on a B200), GB/s read+write:
-    the L2 denominator for the 1024^2 case.  torch is plumbing here (a memcpy and two events)."""
-    try:
-        import torch
-        n = 16 << 20
-        a = torch.empty(n, dtype=torch.uint8, device="cuda")
-        b = torch.empty(n, dtype=torch.uint8, device="cuda")
-        for _ in range(20):
-            b.copy_(a)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        best = None
-        for _ in range(5):
-            e0.record()
-            for _ in range(200):
-                b.copy_(a)
-            e1.record()
-            torch.cuda.synchronize()
-            ms = e0.elapsed_time(e1) / 200
-            best = ms if best is None else min(best, ms)
-        return 2.0 * n / (best / 1e3) / 1e9
-    except Exception:
-        return None
-
-
 def time_shipped_1024(lbm, peak):
     """the reference's shipped 1024x1024 case, all 20000 steps, state initialised on the device"""
     case = cases.shipped("1024x1024")
@@ -305,13 +288,13 @@ def time_shipped_1024(lbm, peak):
         cfg = lat.config
     mlups = case.cells * 20000 / (best / 1e3) / 1e6
     achieved = mlups * 1e6 * BYTES_PER_UPDATE / 1e9
-    l2 = l2_copy_bandwidth()
+    l2 = lbm.probe_l2_copy()
     return {"workload": "reference's shipped 1024x1024 case, all 20000 steps, best of 3",
             "value": mlups, "unit": "MLUPS", "ms_per_step": best / 20000, "bound": "l2 (75.5 MB of state, "
             "double-buffered, lives in the 126 MB L2; DRAM sees ~0.1 MB per step, profiles/r1_ncu_warm_dram_1024x1024.csv)",
             "achieved": achieved, "unit_bw": "GB/s", "peak_hbm": peak, "frac": achieved / peak,
             "frac_hbm": achieved / peak, "peak_l2": l2, "frac_l2": (achieved / l2) if l2 else None,
-            "peak_l2_source": "device-to-device copy of 2 x 16 MiB measured in this run (read + write bytes)",
+            "peak_l2_source": "lbm_probe_l2_copy: read + write copy of 2 x 24 MiB (L2-resident), 200 passes inside one launch, measured in this run",
             "kernel": "lbm_step_kernel<4,128>", "algorithmic_bytes_per_update": BYTES_PER_UPDATE,
             "north_star_target_frac_hbm": 0.75, "engine": cfg}
 
@@ -390,10 +373,9 @@ def main():
     lbm = importlib.import_module("hpc-lattice-boltzmann_b200")
     lbm.load()                                    # loud failure if the CUDA library is missing
     R = Ranks(lbm)
-    uid = R.unique_id()
 
     # ---- device-resident throughput ("value") ---------------------------------------------
-    lat, rows = make_lattice(lbm, R, nx, ny, uid)
+    lat, rows = make_lattice(lbm, R, nx, ny)
     sampler = ClockSampler(local) if rank == 0 else None
     samples, launches = timed_runs(lat, R, a.steps, a.warmup, a.repeats)
     clocks = sampler.stop() if sampler else None
@@ -437,7 +419,7 @@ def main():
             # the north-star's per-step allreduce of the speed sum, done by the step kernel itself
             os.environ["LBM_REDUCE"] = "step"
             try:
-                lat2, _ = make_lattice(lbm, R, nx, ny, uid)
+                lat2, _ = make_lattice(lbm, R, nx, ny)
                 s2, _l = timed_runs(lat2, R, a.steps, a.warmup, min(a.repeats, 7))
                 av2 = lat2.run(8)
                 cfg2 = lat2.config
@@ -456,7 +438,7 @@ def main():
         # <nx>x<ny> naming), 36 GiB of state in total
         try:
             lx, ly = 8192, 65536
-            lat5, _ = make_lattice(lbm, R, lx, ly, uid)
+            lat5, _ = make_lattice(lbm, R, lx, ly)
             s5, _l = timed_runs(lat5, R, 100, 10, 5)
             cfg5 = lat5.config
             lat5.close()
@@ -469,11 +451,14 @@ def main():
         except Exception as e:      # e.g. not enough memory on a small box: say so, keep the headline
             extra["8192x65536"] = {"error": str(e)[:300]}
         R.barrier()
+        if R.dist is not None:
+            R.torch.cuda.synchronize()
+        R.cpu_barrier()
         if rank == 0:
             # the C product on the same workload (all N GPUs driven by ONE host thread of one process);
-            # the other ranks idle at the barrier below
+            # the other ranks idle at the CPU-side barrier below, their GPUs untouched
             extra["exe"] = run_exe(lbm, nx, ny, a.steps, world)
-        R.barrier()
+        R.cpu_barrier()
 
     if rank != 0:
         R.close()

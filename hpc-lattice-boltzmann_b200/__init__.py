@@ -64,6 +64,7 @@ def load():
         "lbm_tot_cells": (C.c_longlong, [vp]),
         "lbm_local_slab": (C.c_int, [vp, ip, ip]),
         "lbm_config_string": (C.c_char_p, [vp]),
+        "lbm_probe_l2_copy": (C.c_int, [C.c_ulonglong, C.c_int, dp]),
         "lbm_host_alloc": (C.c_int, [C.POINTER(vp), C.c_ulonglong]),
         "lbm_host_free": (None, [vp]),
         "lbm_last_error": (C.c_char_p, []),
@@ -218,6 +219,13 @@ def slab_rows(ny, world, rank):
     y0, rows = C.c_int(), C.c_int()
     _check(load().lbm_slab_rows(ny, world, rank, C.byref(y0), C.byref(rows)), "lbm_slab_rows")
     return y0.value, rows.value
+
+
+def probe_l2_copy(nbytes=24 << 20, reps=200):
+    """GB/s (read + write) of an L2-resident device-to-device copy, one launch"""
+    v = C.c_double()
+    _check(load().lbm_probe_l2_copy(nbytes, reps, C.byref(v)), "lbm_probe_l2_copy")
+    return v.value
 
 
 def device_count():

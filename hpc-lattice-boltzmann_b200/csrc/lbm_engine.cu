@@ -1447,6 +1447,36 @@ int lbm_local_slab(const lbm_lattice* h, int* y0, int* rows)
   return 0;
 }
 
+int lbm_probe_l2_copy(unsigned long long bytes, int reps, double* gbs)
+{
+  if (!gbs || bytes < 4096 || reps < 1) return fail("lbm_probe_l2_copy: bad arguments");
+  float4 *a = nullptr, *b = nullptr;
+  const long long n4 = (long long)(bytes / 16);
+  CK(cudaMalloc(&a, (size_t)n4 * 16));
+  CK(cudaMalloc(&b, (size_t)n4 * 16));
+  CK(cudaMemset(a, 0, (size_t)n4 * 16));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  lbm::l2_copy_probe_kernel<<<148 * 8, 256>>>(a, b, n4, 2);          // warm-up: both buffers into L2
+  float best = 0;
+  for (int k = 0; k < 3; k++) {
+    CK(cudaEventRecord(e0));
+    lbm::l2_copy_probe_kernel<<<148 * 8, 256>>>(a, b, n4, reps);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    best = (k == 0 || ms < best) ? ms : best;
+  }
+  *gbs = 2.0 * (double)n4 * 16.0 * reps / (best / 1e3) / 1e9;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(a);
+  cudaFree(b);
+  return 0;
+}
+
 int lbm_host_alloc(void** out, unsigned long long bytes)
 {
   if (!out) return fail("null argument");

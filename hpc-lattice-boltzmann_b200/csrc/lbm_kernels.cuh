@@ -573,6 +573,20 @@ __global__ void macroscopic_kernel(const float* buf, const uint8_t* flags, long 
   }
 }
 
+// measurement aid (bench.py's L2 roofline for the 1024^2 case): `reps` passes of a read + write copy
+// over two buffers small enough to live in L2, inside ONE launch (no launch overhead in the figure)
+__global__ void l2_copy_probe_kernel(const float4* __restrict__ a, float4* __restrict__ b, long long n4, int reps)
+{
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (int r = 0; r < reps; r++) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+      float4 v = __ldcg(a + i);
+      v.x += (float)r;                 // keeps the compiler from collapsing the passes
+      __stcg(b + i, v);
+    }
+  }
+}
+
 // ---- cross-GPU step ordering (one process per GPU: peers are other processes' memory mapped
 // through CUDA IPC, so stream events cannot order them) ---------------------------------------
 // Each rank owns two counters that its ring neighbours bump after every completed step.  Before

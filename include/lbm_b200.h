@@ -102,6 +102,11 @@ long long   lbm_tot_cells(const lbm_lattice* h);
 int         lbm_local_slab(const lbm_lattice* h, int* y0, int* rows);
 const char* lbm_config_string(const lbm_lattice* h);
 
+/* measurement aid: GB/s (read + write) of a device-to-device copy of two `bytes`-sized buffers repeated
+ * `reps` times inside one launch; with 2 x bytes well below the 126 MB L2 this is the L2 bandwidth that
+ * bounds a lattice small enough to live there (the 1024 x 1024 case) */
+int lbm_probe_l2_copy(unsigned long long bytes, int reps, double* gbs);
+
 /* pinned host memory for callers that want full-speed transfers (optional) */
 int  lbm_host_alloc(void** out, unsigned long long bytes);
 void lbm_host_free(void* p);
