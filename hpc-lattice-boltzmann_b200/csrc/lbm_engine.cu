@@ -588,6 +588,14 @@ int launch_stream(lbm_lattice* h, Slab& s, int cur, int fuse_last, int slot, lon
     a.ring_tickets = s.sync + 4;
     a.ring_timeout = s.sync + 2;
     a.ring_phase = h->phase;
+    int n_lo = 0, n_hi = 0;      // the kernel's own conditions, counted over the rows of tiles
+    for (int by = 0; by < s.tiles_y; by++) {
+      const int oy0 = G + by * s.tile_h, oy1 = std::min(oy0 + s.tile_h, G + s.rows);
+      n_lo += oy0 < 2 * G;
+      n_hi += oy1 > s.rows;
+    }
+    a.ring_n_lo = n_lo * s.tiles_x;
+    a.ring_n_hi = n_hi * s.tiles_x;
   }
   lbm::StepReduce r;
   fill_reduce(h, s, r, step_index);

@@ -464,13 +464,18 @@ def _torchrun(world, script_args, env, timeout=300):
     return subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=timeout)
 
 
-@pytest.mark.parametrize("world,fuse,reduce", [(2, 2, "batched"), (3, 2, "batched"), (8, 2, "batched"),
-                                               (2, 3, "batched"), (4, 4, "batched"), (8, 3, "step"),
-                                               (2, 2, "step"), (4, 2, "step")])
-def test_stream_passes_one_process_per_gpu(lbm, world, fuse, reduce):
+@pytest.mark.parametrize("world,fuse,reduce,tile_h", [
+    (2, 2, "batched", None), (3, 2, "batched", None), (8, 2, "batched", None), (2, 3, "batched", None),
+    (4, 4, "batched", None), (8, 3, "step", None), (2, 2, "step", None), (4, 2, "step", None),
+    # tiles shorter than the ghost depth: several rows of tiles touch a slab's ghost zones and all of
+    # them take part in the ring ordering
+    (2, 2, "batched", 2), (2, 3, "step", 2), (2, 4, "batched", 2), (8, 3, "batched", 2)])
+def test_stream_passes_one_process_per_gpu(lbm, world, fuse, reduce, tile_h):
     if _gpus(lbm) < world:
         pytest.skip("needs %d GPUs" % world)
     env = dict(os.environ, LBM_FUSE=str(fuse), LBM_CHUNK="12")
+    if tile_h is not None:
+        env["LBM_TILE_H"] = str(tile_h)
     if reduce == "step":
         env["LBM_REDUCE"] = "step"
     r = _torchrun(world, ["--nx", "512", "--ny", "%d" % (50 * world + 3), "--steps", "41"], env)
