@@ -216,7 +216,7 @@ struct Slab {
   double*    allred_peer[MAX_WORLD] = {};
   long long  allred_cap = 0;
   int        np = 0;               // partial-sum slots per step
-  int        tiles_x = 0, tiles_y = 0, tile_h = 0;
+  int        tiles_x = 0, tiles_y = 0, tile_h = 0, tall_rows = 0, tile_h2 = 0;
   CUtensorMap tm_state, tm_flags;
   double*    partials = nullptr;   // [chunk][np]
   double*    totals = nullptr;     // [totals_cap] per-step speed totals of this slab
@@ -231,6 +231,16 @@ struct Slab {
   bool       owns_accel_row = false;
   int        accel_row = 0;        // storage row of global row ny-2
 };
+
+// first / one-past-last output row (storage index) of row `by` of tiles of the streaming kernel
+int tile_row0(const Slab& s, int by)
+{
+  return by < s.tall_rows ? G + s.tile_h * by : G + s.tile_h * s.tall_rows + s.tile_h2 * (by - s.tall_rows);
+}
+int tile_row1(const Slab& s, int by)
+{
+  return std::min(tile_row0(s, by) + (by < s.tall_rows ? s.tile_h : s.tile_h2), G + s.rows);
+}
 
 const int LO_PLANES[3] = {4, 7, 8};   // pulled by the row below (kernels.cl:94,97,98)
 const int HI_PLANES[3] = {2, 5, 6};   // pulled by the row above (kernels.cl:92,95,96)
@@ -263,6 +273,7 @@ struct lbm_lattice {
   int vec = 4, tpb = 128, chunk = 128, pad = 0;
   bool use_graph = true;
   bool use_pdl = false;        // programmatic dependent launch between consecutive steps (1 GPU)
+  bool stream_pdl = true;      // ... between consecutive streaming passes (LBM_STREAM_PDL)
   int fuse_mode = -1;          // LBM_FUSE: S >= 2 timesteps per pass, 1 = one-step kernel only, -1 = by slab size
   int stream_cfg = 0;          // index into STREAM_CFGS (fixed at create: tiles and TMA boxes depend on it)
   int tile_h_max = 0;          // LBM_TILE_H: upper bound of the tile height (0 = default)
@@ -523,11 +534,22 @@ int stream_steps(const lbm_lattice* h)
 
 template <int S, int NW, int K0, int MINB>
 int launch_stream_t(const CUtensorMap& ts, const CUtensorMap& tf, const StreamArgs& a, const lbm::StepReduce& r,
-                    int ntiles, cudaStream_t st)
+                    int ntiles, cudaStream_t st, bool pdl)
 {
   constexpr int SMEM = lbm::stream_smem_bytes(S, NW, K0);
-  lbm::lbm_stream_kernel<S, NW, K0, MINB><<<ntiles, (S * NW + 1) * 32, SMEM, st>>>(ts, tf, a, r);
-  CK(cudaGetLastError());
+  // programmatic dependent launch: the next pass's blocks are scheduled while this pass's last tiles
+  // are still running and park at griddepcontrol.wait (kernel prologue) until it has completed
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)ntiles);
+  cfg.blockDim = dim3((S * NW + 1) * 32);
+  cfg.dynamicSmemBytes = SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CK(cudaLaunchKernelEx(&cfg, lbm::lbm_stream_kernel<S, NW, K0, MINB>, ts, tf, a, r));
   return 0;
 }
 
@@ -558,7 +580,7 @@ cudaError_t configure_stream(int cfg)
 }
 
 // t -> t+S on every owned row of buffer cur^1 (+ the neighbours' ghost zones); slots: S steps
-int launch_stream(lbm_lattice* h, Slab& s, int cur, int fuse_last, int slot, long long step_index)
+int launch_stream(lbm_lattice* h, Slab& s, int cur, int fuse_last, int slot, long long step_index, bool pdl)
 {
   StreamArgs a{};
   a.src = s.buf[cur];
@@ -570,6 +592,8 @@ int launch_stream(lbm_lattice* h, Slab& s, int cur, int fuse_last, int slot, lon
   a.tiles_x = s.tiles_x;
   a.tiles_y = s.tiles_y;
   a.tile_h = s.tile_h;
+  a.tall_rows = s.tall_rows;
+  a.tile_h2 = s.tile_h2;
   a.src_plane0 = 9 * cur;
   a.omega = h->p.omega;
   a.a1 = h->a1;
@@ -590,9 +614,8 @@ int launch_stream(lbm_lattice* h, Slab& s, int cur, int fuse_last, int slot, lon
     a.ring_phase = h->phase;
     int n_lo = 0, n_hi = 0;      // the kernel's own conditions, counted over the rows of tiles
     for (int by = 0; by < s.tiles_y; by++) {
-      const int oy0 = G + by * s.tile_h, oy1 = std::min(oy0 + s.tile_h, G + s.rows);
-      n_lo += oy0 < 2 * G;
-      n_hi += oy1 > s.rows;
+      n_lo += tile_row0(s, by) < 2 * G;
+      n_hi += tile_row1(s, by) > s.rows;
     }
     a.ring_n_lo = n_lo * s.tiles_x;
     a.ring_n_hi = n_hi * s.tiles_x;
@@ -600,7 +623,7 @@ int launch_stream(lbm_lattice* h, Slab& s, int cur, int fuse_last, int slot, lon
   lbm::StepReduce r;
   fill_reduce(h, s, r, step_index);
   const int nt = s.tiles_x * s.tiles_y;
-#define LBM_CALL(S, NW, K0, MINB) launch_stream_t<S, NW, K0, MINB>(s.tm_state, s.tm_flags, a, r, nt, s.stream)
+#define LBM_CALL(S, NW, K0, MINB) launch_stream_t<S, NW, K0, MINB>(s.tm_state, s.tm_flags, a, r, nt, s.stream, pdl)
   LBM_STREAM_DISPATCH(h->stream_cfg, LBM_CALL)
 #undef LBM_CALL
 }
@@ -672,7 +695,7 @@ int run_steps(lbm_lattice* h, int iters, long long step0, bool last_segment)
         const int fuse_last = (remaining - S * (j + 1) + more) > 0;
         for (auto& s : h->slabs) {
           CK(cudaSetDevice(s.device));
-          if (launch_stream(h, s, cur, fuse_last, S * j, step)) return 1;
+          if (launch_stream(h, s, cur, fuse_last, S * j, step, h->stream_pdl && j > 0)) return 1;
         }
         h->phase++;
         h->last_launches += (long long)nslab;
@@ -848,37 +871,36 @@ void read_tuning(lbm_lattice* h)
   h->stream_cfg = std::min(N_STREAM_CFGS - 1, std::max(0, cfg));
   if (h->fuse_mode >= 2) h->fuse_mode = STREAM_CFGS[h->stream_cfg].s;
   h->tile_h_max = std::max(0, env_int("LBM_TILE_H", 0));
+  h->stream_pdl = env_int("LBM_STREAM_PDL", 1) != 0;
   h->reduce_per_step = env_is("LBM_REDUCE", "step") && h->world > 1 && h->world <= lbm::MAX_REDUCE_WORLD;
   h->stall_test = env_int("LBM_TEST_RING_STALL", -1) >= 0;
 }
 
-// tile height of the streaming kernel: as tall as allowed (the S-1 extra rows above and below a
-// tile are recomputed by its neighbours), but such that the grid is close to a whole number of
-// waves of (SMs x blocks per SM) -- every tile costs the same, so a ragged last wave is idle time
+// Tile heights of the streaming kernel.  A tile recomputes S-1 rows of each vertical neighbour and
+// pays a pipeline fill, so tiles should be tall; but every tile costs the same and the hardware hands
+// them out in index order, so with tall tiles only the end of a pass leaves SMs idle for up to a whole
+// tile (6 % of a pass on a 16384 x 2048 slab).  Hence two zones: tall tiles (tile_h) first, and the
+// last ~1.5 waves' worth of rows in short tiles (tile_h2), which fill the tail.  All heights are
+// whole batches of NW rows.  Decided from the ring's smallest slab, so every slab uses the same heights.
 void choose_tiles(const lbm_lattice* h, Slab& s, int min_rows)
 {
   const StreamCfg& c = STREAM_CFGS[h->stream_cfg];
   const int nx = h->p.nx;
   s.tiles_x = (nx + lbm::S_OUT_W - 1) / lbm::S_OUT_W;
   const int extra = 2 * (c.s - 1);
-  const int hmax = h->tile_h_max > 0 ? h->tile_h_max : 32 * c.nw - extra;
-  const int slots = 148 * c.minb;
-  int best_h = 0;
-  double best_cost = 0;
-  // decided from the ring's smallest slab so that every slab uses the same height
-  for (int ty = (min_rows + hmax - 1) / hmax; ty <= min_rows; ty++) {
-    int hh = (min_rows + ty - 1) / ty;
-    hh = ((hh + extra + c.nw - 1) / c.nw) * c.nw - extra;      // whole batches
-    if (hh < 1) hh = c.nw > extra ? c.nw - extra : c.nw;
-    if (hh > hmax && best_h) break;
-    const int tiles = s.tiles_x * ((min_rows + hh - 1) / hh);
-    const int waves = (tiles + slots - 1) / slots;
-    const double cost = (double)waves * (hh + extra + 6);       // + per-tile prologue, in row units
-    if (!best_h || cost < best_cost) { best_h = hh; best_cost = cost; }
-    if (hh * 3 < hmax) break;                                  // not below a third of the maximum
+  auto whole_batches = [&](int hh) { return std::max(((hh + extra + c.nw - 1) / c.nw) * c.nw - extra, 1); };
+  if (h->tile_h_max > 0) {                        // LBM_TILE_H: one height everywhere
+    s.tile_h = s.tile_h2 = whole_batches(h->tile_h_max);
+    s.tall_rows = 0;
+  } else {
+    s.tile_h = whole_batches(32 * c.nw - extra - c.nw + 1);      // 126 rows for S = 2, NW = 4
+    s.tile_h2 = whole_batches(std::max(8 * c.nw - extra - c.nw + 1, 8));
+    const int slots = 148 * c.minb;
+    const int reserve = (3 * slots / (2 * s.tiles_x) + 1) * s.tile_h2;     // ~1.5 waves of short tiles
+    s.tall_rows = std::max(0, (min_rows - reserve) / s.tile_h);
   }
-  s.tile_h = std::max(best_h, 1);
-  s.tiles_y = (s.rows + s.tile_h - 1) / s.tile_h;
+  const int rest = s.rows - s.tall_rows * s.tile_h;
+  s.tiles_y = s.tall_rows + (std::max(rest, 0) + s.tile_h2 - 1) / s.tile_h2;
 }
 
 int make_tensor_maps(const lbm_lattice* h, Slab& s)
@@ -1008,7 +1030,7 @@ void wire_ghosts(Slab& s, int nx, char* lo_base, int lo_rows, long long lo_ps, c
 
 void set_config_string(lbm_lattice* h)
 {
-  char cfg[400], stream[96] = "";
+  char cfg[480], stream[160] = "";
   const int S = stream_steps(h);
   const bool multi = h->world > 1;
   const char* red = (multi && h->reduce_per_step) ? " reduce=in-kernel-allreduce-per-step" : "";
@@ -1020,8 +1042,9 @@ void set_config_string(lbm_lattice* h)
                                                               : "one-process+peer-stores+wait/signal-kernels");
   if (S > 1) {
     const StreamCfg& c = STREAM_CFGS[h->stream_cfg];
-    snprintf(stream, sizeof stream, " stream=tma(S=%d,nw=%d,stages=%d,blocks/sm=%d) tile=%dx%d",
-             c.s, c.nw, c.k0, c.minb, lbm::S_OUT_W, h->slabs[0].tile_h);
+    snprintf(stream, sizeof stream, " stream=tma(S=%d,nw=%d,stages=%d,blocks/sm=%d,pdl=%d) tile=%dx%d*%d+%dx%d*%d",
+             c.s, c.nw, c.k0, c.minb, (int)h->stream_pdl, lbm::S_OUT_W, h->slabs[0].tile_h, h->slabs[0].tall_rows,
+             lbm::S_OUT_W, h->slabs[0].tile_h2, h->slabs[0].tiles_y - h->slabs[0].tall_rows);
   }
   // graph replay and PDL apply to the one-step kernel on one GPU only
   const bool one_step_only = S == 1 && !multi;
