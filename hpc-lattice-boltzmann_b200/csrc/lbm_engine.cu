@@ -177,15 +177,18 @@ struct Comm {
 
 // tile shapes of the streaming kernel: {timesteps per pass, warps (= rows per batch) per group,
 // TMA stages, blocks per SM}
-struct StreamCfg { int s, nw, k0, minb; };
+struct StreamCfg { int s, nw, k0, minb; bool prod; };
 const StreamCfg STREAM_CFGS[] = {
-    {2, 4, 3, 2},   // 0: 288 threads, 102 KB: two blocks per SM
-    {3, 6, 3, 1},   // 1: 608 threads, 213 KB
-    {2, 8, 3, 1},   // 2: 544 threads, 194 KB
-    {4, 4, 2, 1},   // 3: 544 threads, 176 KB
-    {2, 3, 2, 3},   // 4: 224 threads, 65 KB: three blocks per SM
-    {2, 4, 2, 2},   // 5: as 0 with two TMA stages
-    {3, 4, 2, 1},   // 6: 416 threads, 130 KB
+    {2, 4, 3, 2, true},    // 0: 288 threads, 102 KB of shared memory: two blocks per SM
+    {3, 6, 3, 1, true},    // 1: 608 threads, 213 KB
+    {2, 8, 3, 1, true},    // 2: 544 threads, 195 KB
+    {4, 4, 2, 1, true},    // 3: 544 threads, 176 KB
+    {2, 3, 2, 3, true},    // 4: 224 threads, 65 KB: three blocks per SM
+    {2, 4, 2, 2, true},    // 5: as 0 with two TMA stages
+    {3, 4, 2, 1, true},    // 6: 416 threads, 130 KB
+    {2, 4, 3, 2, false},   // 7: as 0 without the producer warp (group 1 refills): 256 threads, 128 registers
+    {2, 4, 4, 2, false},   // 8: as 7 with four TMA stages (121 KB: ONE block per SM)
+    {2, 8, 3, 1, false},   // 9: as 2 without the producer warp: 512 threads
 };
 constexpr int N_STREAM_CFGS = sizeof(STREAM_CFGS) / sizeof(STREAM_CFGS[0]);
 
@@ -217,7 +220,8 @@ struct Slab {
   long long  allred_cap = 0;
   int        np = 0;               // partial-sum slots per step
   int        tiles_x = 0, tiles_y = 0, tile_h = 0, tall_rows = 0, tile_h2 = 0;
-  CUtensorMap tm_state, tm_flags;
+  CUtensorMap tm_state, tm_flags;       // tile boxes: 128 columns (flags: 144) x NW rows
+  CUtensorMap tm_state_w, tm_flags_w;   // periodic-wrap boxes: 4 columns (flags: 16) x NW rows
   double*    partials = nullptr;   // [chunk][np]
   double*    totals = nullptr;     // [totals_cap] per-step speed totals of this slab
   long long* counter = nullptr;
@@ -225,6 +229,7 @@ struct Slab {
   int        nblk = 0;
   long long  nvec = 0;
   float*     macro = nullptr;      // lbm_macroscopic scratch (4 planes), allocated on first use
+  unsigned long long* trace = nullptr;   // LBM_STREAM_TRACE: per-tile timestamps of the latest streaming pass
   cudaStream_t stream = nullptr;
   cudaEvent_t  ev_begin = nullptr, ev_end = nullptr;
   cudaGraphExec_t graph[2] = {nullptr, nullptr};
@@ -532,16 +537,15 @@ int stream_steps(const lbm_lattice* h)
   return ((long long)min_rows * nx >= (8LL << 20)) ? s : 1;
 }
 
-template <int S, int NW, int K0, int MINB>
-int launch_stream_t(const CUtensorMap& ts, const CUtensorMap& tf, const StreamArgs& a, const lbm::StepReduce& r,
-                    int ntiles, cudaStream_t st, bool pdl)
+template <int S, int NW, int K0, int MINB, bool PROD>
+int launch_stream_t(const Slab& sl, const StreamArgs& a, const lbm::StepReduce& r, int ntiles, cudaStream_t st, bool pdl)
 {
   constexpr int SMEM = lbm::stream_smem_bytes(S, NW, K0);
   // programmatic dependent launch: the next pass's blocks are scheduled while this pass's last tiles
   // are still running and park at griddepcontrol.wait (kernel prologue) until it has completed
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)ntiles);
-  cfg.blockDim = dim3((S * NW + 1) * 32);
+  cfg.blockDim = dim3((S * NW + (PROD ? 1 : 0)) * 32);
   cfg.dynamicSmemBytes = SMEM;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -549,32 +553,36 @@ int launch_stream_t(const CUtensorMap& ts, const CUtensorMap& tf, const StreamAr
   attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  CK(cudaLaunchKernelEx(&cfg, lbm::lbm_stream_kernel<S, NW, K0, MINB>, ts, tf, a, r));
+  CK(cudaLaunchKernelEx(&cfg, lbm::lbm_stream_kernel<S, NW, K0, MINB, PROD>, sl.tm_state, sl.tm_flags, sl.tm_state_w,
+                        sl.tm_flags_w, a, r));
   return 0;
 }
 
-template <int S, int NW, int K0, int MINB>
+template <int S, int NW, int K0, int MINB, bool PROD>
 cudaError_t configure_stream_t()
 {
-  return cudaFuncSetAttribute(lbm::lbm_stream_kernel<S, NW, K0, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  return cudaFuncSetAttribute(lbm::lbm_stream_kernel<S, NW, K0, MINB, PROD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               lbm::stream_smem_bytes(S, NW, K0));
 }
 
 #define LBM_STREAM_DISPATCH(idx, CALL)                 \
   switch (idx) {                                       \
-    case 1: return CALL(3, 6, 3, 1);                   \
-    case 2: return CALL(2, 8, 3, 1);                   \
-    case 3: return CALL(4, 4, 2, 1);                   \
-    case 4: return CALL(2, 3, 2, 3);                   \
-    case 5: return CALL(2, 4, 2, 2);                   \
-    case 6: return CALL(3, 4, 2, 1);                   \
-    default: return CALL(2, 4, 3, 2);                  \
+    case 1: return CALL(3, 6, 3, 1, true);             \
+    case 2: return CALL(2, 8, 3, 1, true);             \
+    case 3: return CALL(4, 4, 2, 1, true);             \
+    case 4: return CALL(2, 3, 2, 3, true);             \
+    case 5: return CALL(2, 4, 2, 2, true);             \
+    case 6: return CALL(3, 4, 2, 1, true);             \
+    case 7: return CALL(2, 4, 3, 2, false);            \
+    case 8: return CALL(2, 4, 4, 2, false);            \
+    case 9: return CALL(2, 8, 3, 1, false);            \
+    default: return CALL(2, 4, 3, 2, true);            \
   }
 
 // the opt-in to > 48 KB of dynamic shared memory is a per-device function attribute
 cudaError_t configure_stream(int cfg)
 {
-#define LBM_CALL(S, NW, K0, MINB) configure_stream_t<S, NW, K0, MINB>()
+#define LBM_CALL(S, NW, K0, MINB, PROD) configure_stream_t<S, NW, K0, MINB, PROD>()
   LBM_STREAM_DISPATCH(cfg, LBM_CALL)
 #undef LBM_CALL
 }
@@ -583,7 +591,6 @@ cudaError_t configure_stream(int cfg)
 int launch_stream(lbm_lattice* h, Slab& s, int cur, int fuse_last, int slot, long long step_index, bool pdl)
 {
   StreamArgs a{};
-  a.src = s.buf[cur];
   a.dst = s.buf[cur ^ 1];
   a.flags = s.flags;
   a.ps = s.ps;
@@ -623,7 +630,8 @@ int launch_stream(lbm_lattice* h, Slab& s, int cur, int fuse_last, int slot, lon
   lbm::StepReduce r;
   fill_reduce(h, s, r, step_index);
   const int nt = s.tiles_x * s.tiles_y;
-#define LBM_CALL(S, NW, K0, MINB) launch_stream_t<S, NW, K0, MINB>(s.tm_state, s.tm_flags, a, r, nt, s.stream, pdl)
+  a.trace = s.trace;
+#define LBM_CALL(S, NW, K0, MINB, PROD) launch_stream_t<S, NW, K0, MINB, PROD>(s, a, r, nt, s.stream, pdl)
   LBM_STREAM_DISPATCH(h->stream_cfg, LBM_CALL)
 #undef LBM_CALL
 }
@@ -799,6 +807,21 @@ int run_impl(lbm_lattice* h, int iters, double* av_out)
     ms_max = std::max(ms_max, ms);
   }
   h->last_ms = ms_max;
+  if (const char* path = getenv("LBM_STREAM_TRACE")) {     // tuning aid: the latest pass's tile schedule
+    Slab& s = h->slabs[0];
+    if (s.trace) {
+      const size_t nt = (size_t)s.tiles_x * s.tiles_y;
+      std::vector<unsigned long long> t(4 * nt);
+      CK(cudaMemcpy(t.data(), s.trace, sizeof(unsigned long long) * 4 * nt, cudaMemcpyDeviceToHost));
+      if (FILE* fp = fopen(path, "w")) {
+        fprintf(fp, "tile,bx,by,sm,block,start_ns,end_ns\n");
+        for (size_t i = 0; i < nt; i++)
+          fprintf(fp, "%zu,%zu,%zu,%llu,%llu,%llu,%llu\n", i, i % s.tiles_x, i / s.tiles_x, t[4 * i], t[4 * i + 2],
+                  t[4 * i + 1], t[4 * i + 3]);
+        fclose(fp);
+      }
+    }
+  }
 
   // a neighbour that never showed up: every slab of the ring fails together
   long long timed_out = 0;
@@ -909,25 +932,27 @@ int make_tensor_maps(const lbm_lattice* h, Slab& s)
   if (!enc) return fail("cuTensorMapEncodeTiled is not available from this driver");
   const StreamCfg& c = STREAM_CFGS[h->stream_cfg];
   const cuuint64_t nx = (cuuint64_t)h->p.nx, nrows = (cuuint64_t)(s.rows + 2 * G);
-  {
-    const cuuint64_t dims[3] = {nx, nrows, 18};
-    const cuuint64_t strides[2] = {nx * 4, (cuuint64_t)s.ps * 4};
-    const cuuint32_t box[3] = {(cuuint32_t)lbm::S_TILE_W, (cuuint32_t)c.nw, 1};
-    const cuuint32_t es[3] = {1, 1, 1};
-    const CUresult r = enc(&s.tm_state, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, s.base, dims, strides, box, es,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled (populations) failed with CUresult %d", (int)r);
-  }
-  {
-    const cuuint64_t dims[2] = {nx, nrows};
-    const cuuint64_t strides[1] = {nx};
-    const cuuint32_t box[2] = {(cuuint32_t)lbm::S_FLAG_BOX, (cuuint32_t)c.nw};
-    const cuuint32_t es[2] = {1, 1};
-    const CUresult r = enc(&s.tm_flags, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, s.flags, dims, strides, box, es,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled (flags) failed with CUresult %d", (int)r);
+  for (int wrap = 0; wrap < 2; wrap++) {
+    {
+      const cuuint64_t dims[3] = {nx, nrows, 18};
+      const cuuint64_t strides[2] = {nx * 4, (cuuint64_t)s.ps * 4};
+      const cuuint32_t box[3] = {(cuuint32_t)(wrap ? 4 : lbm::S_TILE_W), (cuuint32_t)c.nw, 1};
+      const cuuint32_t es[3] = {1, 1, 1};
+      const CUresult r = enc(wrap ? &s.tm_state_w : &s.tm_state, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, s.base, dims,
+                             strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled (populations) failed with CUresult %d", (int)r);
+    }
+    {
+      const cuuint64_t dims[2] = {nx, nrows};
+      const cuuint64_t strides[1] = {nx};
+      const cuuint32_t box[2] = {(cuuint32_t)(wrap ? 16 : lbm::S_FLAG_BOX), (cuuint32_t)c.nw};
+      const cuuint32_t es[2] = {1, 1};
+      const CUresult r = enc(wrap ? &s.tm_flags_w : &s.tm_flags, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, s.flags, dims,
+                             strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled (flags) failed with CUresult %d", (int)r);
+    }
   }
   return 0;
 }
@@ -975,6 +1000,10 @@ int create_slab(lbm_lattice* h, Slab& s, const int* obstacles, int row_first, in
     if (e != cudaSuccess) return fail("cudaFuncSetAttribute(shared memory): %s", cudaGetErrorString(e));
   }
   s.np = std::max(s.nblk, s.tiles_x * s.tiles_y);
+  if (getenv("LBM_STREAM_TRACE") && s.tiles_x * s.tiles_y > 0) {
+    CK(cudaMalloc(&s.trace, sizeof(unsigned long long) * 4 * (size_t)s.tiles_x * s.tiles_y));
+    CK(cudaMemsetAsync(s.trace, 0, sizeof(unsigned long long) * 4 * (size_t)s.tiles_x * s.tiles_y, s.stream));
+  }
   CK(cudaMalloc(&s.partials, sizeof(double) * (size_t)h->chunk * s.np));
   CK(cudaMalloc(&s.counter, sizeof(long long)));
   CK(cudaMemsetAsync(s.counter, 0, sizeof(long long), s.stream));
@@ -1030,7 +1059,7 @@ void wire_ghosts(Slab& s, int nx, char* lo_base, int lo_rows, long long lo_ps, c
 
 void set_config_string(lbm_lattice* h)
 {
-  char cfg[480], stream[160] = "";
+  char cfg[520], stream[200] = "";
   const int S = stream_steps(h);
   const bool multi = h->world > 1;
   const char* red = (multi && h->reduce_per_step) ? " reduce=in-kernel-allreduce-per-step" : "";
@@ -1042,8 +1071,8 @@ void set_config_string(lbm_lattice* h)
                                                               : "one-process+peer-stores+wait/signal-kernels");
   if (S > 1) {
     const StreamCfg& c = STREAM_CFGS[h->stream_cfg];
-    snprintf(stream, sizeof stream, " stream=tma(S=%d,nw=%d,stages=%d,blocks/sm=%d,pdl=%d) tile=%dx%d*%d+%dx%d*%d",
-             c.s, c.nw, c.k0, c.minb, (int)h->stream_pdl, lbm::S_OUT_W, h->slabs[0].tile_h, h->slabs[0].tall_rows,
+    snprintf(stream, sizeof stream, " stream=tma(S=%d,nw=%d,stages=%d,blocks/sm=%d,producer=%s,pdl=%d) tile=%dx%d*%d+%dx%d*%d",
+             c.s, c.nw, c.k0, c.minb, c.prod ? "warp" : "group1", (int)h->stream_pdl, lbm::S_OUT_W, h->slabs[0].tile_h, h->slabs[0].tall_rows,
              lbm::S_OUT_W, h->slabs[0].tile_h2, h->slabs[0].tiles_y - h->slabs[0].tall_rows);
   }
   // graph replay and PDL apply to the one-step kernel on one GPU only
@@ -1315,6 +1344,7 @@ void lbm_destroy(lbm_lattice* h)
     if (s.totals) cudaFree(s.totals);
     if (s.counter) cudaFree(s.counter);
     if (s.macro) cudaFree(s.macro);
+    if (s.trace) cudaFree(s.trace);
     if (s.ev_begin) cudaEventDestroy(s.ev_begin);
     if (s.ev_end) cudaEventDestroy(s.ev_end);
     if (s.stream) cudaStreamDestroy(s.stream);
