@@ -177,18 +177,16 @@ struct Comm {
 
 // tile shapes of the streaming kernel: {timesteps per pass, warps (= rows per batch) per group,
 // TMA stages, blocks per SM}
-struct StreamCfg { int s, nw, k0, minb; bool prod; };
+struct StreamCfg { int s, nw, k0, minb; };
+// measured on B200, 16384^2 (profiles/r2_tuning.md): 0: 165.5, 5: 162.1, 2: 159.4, 3: 152.0, 1: 150.1, 6: 140.3 GLUPS
 const StreamCfg STREAM_CFGS[] = {
-    {2, 4, 3, 2, true},    // 0: 288 threads, 102 KB of shared memory: two blocks per SM
-    {3, 6, 3, 1, true},    // 1: 608 threads, 213 KB
-    {2, 8, 3, 1, true},    // 2: 544 threads, 195 KB
-    {4, 4, 2, 1, true},    // 3: 544 threads, 176 KB
-    {2, 3, 2, 3, true},    // 4: 224 threads, 65 KB: three blocks per SM
-    {2, 4, 2, 2, true},    // 5: as 0 with two TMA stages
-    {3, 4, 2, 1, true},    // 6: 416 threads, 130 KB
-    {2, 4, 3, 2, false},   // 7: as 0 without the producer warp (group 1 refills): 256 threads, 128 registers
-    {2, 4, 4, 2, false},   // 8: as 7 with four TMA stages (121 KB: ONE block per SM)
-    {2, 8, 3, 1, false},   // 9: as 2 without the producer warp: 512 threads
+    {2, 4, 3, 2},   // 0: 288 threads, 106 KB of shared memory: two blocks per SM (default)
+    {3, 6, 3, 1},   // 1: 608 threads, 219 KB (default for LBM_FUSE=3)
+    {2, 8, 3, 1},   // 2: 544 threads, 201 KB
+    {4, 4, 2, 1},   // 3: 544 threads, 179 KB (default for LBM_FUSE=4)
+    {2, 3, 2, 3},   // 4: 224 threads, 68 KB: three blocks per SM
+    {2, 4, 2, 2},   // 5: as 0 with two TMA stages
+    {3, 4, 2, 1},   // 6: 416 threads, 133 KB
 };
 constexpr int N_STREAM_CFGS = sizeof(STREAM_CFGS) / sizeof(STREAM_CFGS[0]);
 
@@ -537,7 +535,7 @@ int stream_steps(const lbm_lattice* h)
   return ((long long)min_rows * nx >= (8LL << 20)) ? s : 1;
 }
 
-template <int S, int NW, int K0, int MINB, bool PROD>
+template <int S, int NW, int K0, int MINB>
 int launch_stream_t(const Slab& sl, const StreamArgs& a, const lbm::StepReduce& r, int ntiles, cudaStream_t st, bool pdl)
 {
   constexpr int SMEM = lbm::stream_smem_bytes(S, NW, K0);
@@ -545,7 +543,7 @@ int launch_stream_t(const Slab& sl, const StreamArgs& a, const lbm::StepReduce& 
   // are still running and park at griddepcontrol.wait (kernel prologue) until it has completed
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)ntiles);
-  cfg.blockDim = dim3((S * NW + (PROD ? 1 : 0)) * 32);
+  cfg.blockDim = dim3((S * NW + 1) * 32);
   cfg.dynamicSmemBytes = SMEM;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -553,36 +551,33 @@ int launch_stream_t(const Slab& sl, const StreamArgs& a, const lbm::StepReduce& 
   attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  CK(cudaLaunchKernelEx(&cfg, lbm::lbm_stream_kernel<S, NW, K0, MINB, PROD>, sl.tm_state, sl.tm_flags, sl.tm_state_w,
+  CK(cudaLaunchKernelEx(&cfg, lbm::lbm_stream_kernel<S, NW, K0, MINB>, sl.tm_state, sl.tm_flags, sl.tm_state_w,
                         sl.tm_flags_w, a, r));
   return 0;
 }
 
-template <int S, int NW, int K0, int MINB, bool PROD>
+template <int S, int NW, int K0, int MINB>
 cudaError_t configure_stream_t()
 {
-  return cudaFuncSetAttribute(lbm::lbm_stream_kernel<S, NW, K0, MINB, PROD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  return cudaFuncSetAttribute(lbm::lbm_stream_kernel<S, NW, K0, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               lbm::stream_smem_bytes(S, NW, K0));
 }
 
 #define LBM_STREAM_DISPATCH(idx, CALL)                 \
   switch (idx) {                                       \
-    case 1: return CALL(3, 6, 3, 1, true);             \
-    case 2: return CALL(2, 8, 3, 1, true);             \
-    case 3: return CALL(4, 4, 2, 1, true);             \
-    case 4: return CALL(2, 3, 2, 3, true);             \
-    case 5: return CALL(2, 4, 2, 2, true);             \
-    case 6: return CALL(3, 4, 2, 1, true);             \
-    case 7: return CALL(2, 4, 3, 2, false);            \
-    case 8: return CALL(2, 4, 4, 2, false);            \
-    case 9: return CALL(2, 8, 3, 1, false);            \
-    default: return CALL(2, 4, 3, 2, true);            \
+    case 1: return CALL(3, 6, 3, 1);                   \
+    case 2: return CALL(2, 8, 3, 1);                   \
+    case 3: return CALL(4, 4, 2, 1);                   \
+    case 4: return CALL(2, 3, 2, 3);                   \
+    case 5: return CALL(2, 4, 2, 2);                   \
+    case 6: return CALL(3, 4, 2, 1);                   \
+    default: return CALL(2, 4, 3, 2);                  \
   }
 
 // the opt-in to > 48 KB of dynamic shared memory is a per-device function attribute
 cudaError_t configure_stream(int cfg)
 {
-#define LBM_CALL(S, NW, K0, MINB, PROD) configure_stream_t<S, NW, K0, MINB, PROD>()
+#define LBM_CALL(S, NW, K0, MINB) configure_stream_t<S, NW, K0, MINB>()
   LBM_STREAM_DISPATCH(cfg, LBM_CALL)
 #undef LBM_CALL
 }
@@ -631,7 +626,7 @@ int launch_stream(lbm_lattice* h, Slab& s, int cur, int fuse_last, int slot, lon
   fill_reduce(h, s, r, step_index);
   const int nt = s.tiles_x * s.tiles_y;
   a.trace = s.trace;
-#define LBM_CALL(S, NW, K0, MINB, PROD) launch_stream_t<S, NW, K0, MINB, PROD>(s, a, r, nt, s.stream, pdl)
+#define LBM_CALL(S, NW, K0, MINB) launch_stream_t<S, NW, K0, MINB>(s, a, r, nt, s.stream, pdl)
   LBM_STREAM_DISPATCH(h->stream_cfg, LBM_CALL)
 #undef LBM_CALL
 }
@@ -1071,8 +1066,8 @@ void set_config_string(lbm_lattice* h)
                                                               : "one-process+peer-stores+wait/signal-kernels");
   if (S > 1) {
     const StreamCfg& c = STREAM_CFGS[h->stream_cfg];
-    snprintf(stream, sizeof stream, " stream=tma(S=%d,nw=%d,stages=%d,blocks/sm=%d,producer=%s,pdl=%d) tile=%dx%d*%d+%dx%d*%d",
-             c.s, c.nw, c.k0, c.minb, c.prod ? "warp" : "group1", (int)h->stream_pdl, lbm::S_OUT_W, h->slabs[0].tile_h, h->slabs[0].tall_rows,
+    snprintf(stream, sizeof stream, " stream=tma(S=%d,nw=%d,stages=%d,blocks/sm=%d,pdl=%d) tile=%dx%d*%d+%dx%d*%d",
+             c.s, c.nw, c.k0, c.minb, (int)h->stream_pdl, lbm::S_OUT_W, h->slabs[0].tile_h, h->slabs[0].tall_rows,
              lbm::S_OUT_W, h->slabs[0].tile_h2, h->slabs[0].tiles_y - h->slabs[0].tall_rows);
   }
   // graph replay and PDL apply to the one-step kernel on one GPU only

@@ -66,15 +66,18 @@ struct StepReduce {
   unsigned* ticket;                   // blocks of this launch that are done
 };
 
-// called by every thread of every block after the block's partials are written.  partials:
-// [nsteps][stride], `count` valid entries per step.  scratch: >= NT doubles of shared memory.
+// called by every thread of every block after the block's partials are written (by its threads
+// 0 .. nsteps-1).  partials: [nsteps][stride], `count` valid entries per step.  scratch: >= NT doubles
+// of shared memory.
 template <int NT>
 __device__ __forceinline__ void last_block_allreduce(const StepReduce& R, const double* partials, int stride,
                                                      int count, int nsteps, double* scratch)
 {
   if (R.peer[0] == nullptr) return;
   __shared__ int is_last;
-  __threadfence();
+  // only the threads that wrote partials fence (a fence by every thread would make each block wait
+  // for all of its own population stores to drain before it may leave the SM)
+  if (threadIdx.x < nsteps) __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) is_last = atomicAdd(R.ticket, 1u) == gridDim.x - 1u;
   __syncthreads();
