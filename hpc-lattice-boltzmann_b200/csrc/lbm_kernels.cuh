@@ -9,11 +9,12 @@
 //   av_velocity      kernels.cl:198 + d2q9-bgk.c:408-423 -> fused double-precision tree reduction
 //
 // Layout (DESIGN.md "Data layout"): SoA, 9 planes per buffer, two buffers (ping-pong).  A slab
-// of `rows` lattice rows is stored with one ghost row below (storage row 0) and one above
-// (storage row rows+1), so the y-periodic wrap and the multi-GPU halo are the same mechanism:
-// whoever computes a boundary row also stores the three populations its vertical neighbour will
-// pull into that neighbour's ghost row (which is this GPU's own ghost row when there is one GPU,
-// or a peer pointer over NVLink when there are several).
+// of `rows` lattice rows is stored with GHOST ghost rows below and above; the kernels of this file
+// work on a view whose row 0 is the nearest ghost row below and whose row rows+1 is the nearest one
+// above, so the y-periodic wrap and the multi-GPU halo are the same mechanism: whoever computes a
+// boundary row also stores the three populations its vertical neighbour will pull into that
+// neighbour's ghost row (which is this GPU's own ghost row when there is one GPU, or a peer pointer
+// over NVLink when there are several).  The streaming kernel (lbm_stream.cuh) uses all GHOST rows.
 //
 // Arithmetic contract ("f32-strict"; mirrored bit-for-bit by oracle/canon_impl.h VARIANT_B200):
 // every operation below is written as an explicit round-to-nearest intrinsic, so nvcc can neither
