@@ -25,7 +25,9 @@ What one JSON line holds (beyond the base contract):
                         computes the same thing (the N = 1 path is pinned to the oracle by the tests)
   cpu_baseline          the unmodified reference (oracle/_ref) on the host cores, bounded square crop
   extra                 per-step in-kernel allreduce variant (N > 1), BASELINE.json's config 5
-                        (8192x65536), d2q9-bgk.exe on the same workload with LBM_GPUS=N
+                        (8192x65536), d2q9-bgk.exe on the same workload with LBM_GPUS=N, and (N = 1)
+                        small_cases: the shipped 128x128 / 128x256 / 256x256 cases with the persistent
+                        shared-memory kernel next to the one-step launches
 
 `--impl reference` times the reference's CPU implementation of the path instead (rank 0 only).
 This file is one of the three places allowed to touch oracle/ -- only as the timed CPU baseline.
@@ -299,6 +301,39 @@ def time_shipped_1024(lbm, peak):
             "north_star_target_frac_hbm": 0.75, "engine": cfg}
 
 
+def time_small_cases(lbm):
+    """the reference's shipped 128x128 / 128x256 / 256x256 cases (BASELINE.json configs 1-2), 20000 steps
+    each from the device-side initial state: the persistent shared-memory kernel (the default for
+    lattices this small) next to the one-step launches it replaces (LBM_RESIDENT=0)"""
+    out = {}
+    for name in ("128x128", "128x256", "256x256"):
+        case = cases.shipped(name)
+        row = {}
+        for key, resident in (("persistent", None), ("launches", "0")):
+            saved = os.environ.get("LBM_RESIDENT")
+            if resident is not None:
+                os.environ["LBM_RESIDENT"] = resident
+            try:
+                with lbm.Lattice(case.nx, case.ny, case.density, case.accel, case.omega, case.obstacles) as lat:
+                    lat.init_equilibrium()
+                    lat.run(2000)
+                    best = None
+                    for _ in range(3):
+                        lat.run(20000)
+                        best = lat.last_run_ms if best is None else min(best, lat.last_run_ms)
+                    row[key] = {"us_per_step": best / 20000 * 1e3, "MLUPS": case.cells * 20000 / (best / 1e3) / 1e6,
+                                "launches_per_20000_steps": lat.last_run_launches, "engine": lat.config}
+            finally:
+                if resident is not None:
+                    if saved is None:
+                        os.environ.pop("LBM_RESIDENT", None)
+                    else:
+                        os.environ["LBM_RESIDENT"] = saved
+        row["speedup"] = row["launches"]["us_per_step"] / row["persistent"]["us_per_step"]
+        out[name] = row
+    return out
+
+
 def run_exe(lbm, nx, ny, steps, ngpus):
     """d2q9-bgk.exe <paramfile> <obstaclefile> on the same synthetic workload with LBM_GPUS=ngpus:
     the C product end to end (text parse, device init, run, 4-plane read-back; final_state.dat is
@@ -527,6 +562,10 @@ def main():
         if world == 1:
             line["cpu_baseline"] = time_reference_cpu(nx, ny, a.steps, 1)
             line["roofline_1024"] = time_shipped_1024(lbm, peak)
+            try:
+                extra["small_cases"] = time_small_cases(lbm)
+            except Exception as e:  # noqa: BLE001 -- an extra must not cost the headline
+                extra["small_cases"] = {"error": str(e)[:300]}
         line["extra"] = extra
     emit(line)
     R.close()

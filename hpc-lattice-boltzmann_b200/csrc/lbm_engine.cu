@@ -49,6 +49,7 @@
 #include "../../include/lbm_b200.h"
 #include "lbm_kernels.cuh"
 #include "lbm_stream.cuh"
+#include "lbm_resident.cuh"
 
 namespace {
 
@@ -227,6 +228,7 @@ struct Slab {
   int        nblk = 0;
   long long  nvec = 0;
   float*     macro = nullptr;      // lbm_macroscopic scratch (4 planes), allocated on first use
+  unsigned long long* inbox = nullptr;   // persistent small-lattice kernel: per-block halo inboxes ({tag : float} words)
   unsigned long long* trace = nullptr;   // LBM_STREAM_TRACE: per-tile timestamps of the latest streaming pass
   cudaStream_t stream = nullptr;
   cudaEvent_t  ev_begin = nullptr, ev_end = nullptr;
@@ -284,6 +286,11 @@ struct lbm_lattice {
   bool ring_in_kernel = false; // one-step kernel: counters handled by its boundary blocks (else wait/signal launches)
   bool reduce_per_step = false;// LBM_REDUCE=step
   bool stall_test = false;     // LBM_TEST_RING_STALL: this rank never publishes (negative test of the time-out)
+  // small lattices on one GPU: the whole time loop as one persistent cooperative launch (lbm_resident.cuh)
+  bool resident = false;
+  int res_rows = 1, res_tpb = 512, res_nblk = 0, res_chunk = 1200;   // rows per block, threads, blocks, steps per launch
+  int res_cpt = 1;             // cells per thread (kernel instantiation)
+  unsigned res_base = 0;       // halo tags handed out so far (one per timestep)
   unsigned phase = 0;          // ring phases completed since creation (all slabs advance together)
   bool poisoned = false;       // a run failed half-way: the ring counters are out of step
   double last_ms = 0;
@@ -662,15 +669,89 @@ int launch_one_step(lbm_lattice* h, int cur, int fuse, int slot, long long step_
   return 0;
 }
 
+// ---- the persistent small-lattice kernel (lbm_resident.cuh) ---------------------------------------
+// `n` timesteps from buffer `cur` into buffer cur^1 in one cooperative launch; partial sums of step i
+// go to slot i
+int launch_resident(lbm_lattice* h, Slab& s, int cur, int n, int fuse_after)
+{
+  lbm::ResidentArgs a{};
+  a.src = s.buf[cur];
+  a.dst = s.buf[cur ^ 1];
+  a.flags = s.flags;
+  a.ps = s.ps;
+  a.nx = h->p.nx;
+  a.ny = s.rows;
+  a.R = h->res_rows;
+  a.nsteps = n;
+  a.fuse_after = fuse_after;
+  a.np = s.np;
+  a.omega = h->p.omega;
+  a.a1 = h->a1;
+  a.a2 = h->a2;
+  a.partials = s.partials;
+  a.inbox = s.inbox;
+  a.base = h->res_base;
+  a.timed_out = s.sync + 2;
+  a.stall_block = env_int("LBM_TEST_RESIDENT_STALL", -1);
+#ifdef LBM_RES_TRACE
+  static long long* trace = nullptr;
+  if (!trace) { CK(cudaMallocManaged(&trace, sizeof(long long) * 2 * 16 * 6)); memset(trace, 0, sizeof(long long) * 192); }
+  a.trace = trace;
+  if (const char* path = getenv("LBM_RES_TRACE_FILE")) {      // dump what the PREVIOUS launch recorded
+    cudaStreamSynchronize(s.stream);
+    if (FILE* fp = fopen(path, "w")) {
+      for (int th = 0; th < 2; th++)
+        for (int i = 0; i < 16; i++) {
+          const long long* r = trace + (th * 16 + i) * 6;
+          fprintf(fp, "thread %s step %d: compute+send %lld  poll %lld  barrier %lld  reduce %lld | step %lld\n", th ? "last" : "0", 64 + i,
+                  r[1] - r[0], r[2] - r[1], r[3] - r[2], r[4] - r[3], i ? r[0] - (r - 6)[0] : 0LL);
+        }
+      fclose(fp);
+    }
+  }
+#endif
+  h->res_base += (unsigned)n;
+  h->last_launches++;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)h->res_nblk);
+  cfg.blockDim = dim3((unsigned)h->res_tpb);
+  cfg.dynamicSmemBytes = lbm::resident_smem_bytes(h->res_rows, h->p.nx, h->res_tpb);
+  cfg.stream = s.stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;      // all blocks co-resident, or the launch fails
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  switch (h->res_cpt) {
+    case 1: CK(cudaLaunchKernelEx(&cfg, lbm::lbm_resident_kernel<1>, a)); break;
+    case 2: CK(cudaLaunchKernelEx(&cfg, lbm::lbm_resident_kernel<2>, a)); break;
+    case 4: CK(cudaLaunchKernelEx(&cfg, lbm::lbm_resident_kernel<4>, a)); break;
+    default: CK(cudaLaunchKernelEx(&cfg, lbm::lbm_resident_kernel<8>, a)); break;
+  }
+  return 0;
+}
+
+// shared-memory opt-in and co-residency of the instantiation for `cpt` cells per thread
+int resident_prepare(int cpt, int tpb, size_t smem, int* blocks_per_sm)
+{
+  const void* fn = cpt == 1 ? (const void*)lbm::lbm_resident_kernel<1>
+                   : cpt == 2 ? (const void*)lbm::lbm_resident_kernel<2>
+                   : cpt == 4 ? (const void*)lbm::lbm_resident_kernel<4>
+                              : (const void*)lbm::lbm_resident_kernel<8>;
+  CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, fn, tpb, smem));
+  return 0;
+}
+
 // second stage of the reduction for the `nsteps` steps just launched; their partials are per tile
-// (streaming passes) or per block (one-step launches)
-int reduce_chunk(lbm_lattice* h, int nsteps, bool tiles)
+// (streaming passes) or per block (one-step launches: count = 0; persistent kernel: its block count)
+int reduce_chunk(lbm_lattice* h, int nsteps, bool tiles, int count = 0)
 {
   if (h->reduce_per_step) return 0;     // done by the last block of every launch
   for (auto& s : h->slabs) {
     CK(cudaSetDevice(s.device));
     lbm::reduce_partials_kernel<<<nsteps, 256, 0, s.stream>>>(s.partials, s.np,
-                                                             tiles ? s.tiles_x * s.tiles_y : s.nblk,
+                                                             count ? count : tiles ? s.tiles_x * s.tiles_y : s.nblk,
                                                              s.totals, s.counter);
     CK(cudaGetLastError());
     lbm::advance_counter_kernel<<<1, 1, 0, s.stream>>>(s.counter, nsteps);
@@ -707,6 +788,21 @@ int run_steps(lbm_lattice* h, int iters, long long step0, bool last_segment)
       }
       if (reduce_chunk(h, S * passes, true)) return 1;
       remaining -= S * passes;
+    }
+  }
+
+  // small lattice on one GPU: the remaining steps as persistent launches of up to res_chunk steps (a
+  // single step -- lbm_step -- stays a plain launch)
+  if (h->resident && remaining >= 2) {
+    Slab& s = h->slabs[0];
+    CK(cudaSetDevice(s.device));
+    while (remaining > 0) {
+      const int n = std::min(remaining, h->res_chunk);
+      if (launch_resident(h, s, cur, n, (remaining - n + more) > 0)) return 1;
+      if (reduce_chunk(h, n, false, h->res_nblk)) return 1;
+      cur ^= 1;                       // a launch reads one buffer and leaves its result in the other
+      remaining -= n;
+      step += n;
     }
   }
 
@@ -835,6 +931,17 @@ int run_impl(lbm_lattice* h, int iters, double* av_out)
     }
   }
 
+  if (h->resident) {
+    unsigned t = 0;
+    Slab& s = h->slabs[0];
+    CK(cudaSetDevice(s.device));
+    CK(cudaMemcpy(&t, s.sync + 2, sizeof t, cudaMemcpyDeviceToHost));
+    if (t) {
+      h->poisoned = true;
+      return fail("lbm_run: the persistent kernel timed out waiting for a neighbouring block's halo");
+    }
+  }
+
   if (!h->reduce_per_step) {
     tmp.resize((size_t)iters);
     if (!comm) {
@@ -952,6 +1059,46 @@ int make_tensor_maps(const lbm_lattice* h, Slab& s)
   return 0;
 }
 
+// Small lattice on one GPU: can the time loop be the persistent kernel?  Block b keeps R whole rows in
+// shared memory (two copies) and all blocks must be resident at once -- one block per SM, so
+// R = ceil(ny / SMs) -- which bounds the lattice at roughly (9R + 6) * nx * 8 bytes <= 227 KB per block:
+// 512 x 512 fits, 1024 x 1024 does not (and does not need it: its steps are 10 us of real work).
+int decide_resident(lbm_lattice* h, Slab& s)
+{
+  const int mode = env_int("LBM_RESIDENT", -1);       // 0 never, 1 whenever it fits, -1 auto
+  if (mode == 0) return 0;
+  const int nx = h->p.nx, ny = s.rows;
+  if (mode < 0 && (long long)nx * ny > (long long)env_int("LBM_RESIDENT_MAX_CELLS", 1 << 19)) return 0;
+  int sms = 0, coop = 0, smem_max = 0;
+  CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s.device));
+  CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, s.device));
+  CK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, s.device));
+  if (!coop || sms < 1) return 0;
+  int R = std::max((ny + sms - 1) / sms, env_int("LBM_RES_ROWS", 1));
+  R = std::min(R, ny);
+  int tpb = std::min(512, std::max(32, env_int("LBM_RES_TPB", 512)));
+  tpb = std::min(tpb, (R * nx + 31) / 32 * 32) / 32 * 32;
+  const size_t smem = lbm::resident_smem_bytes(R, nx, tpb);
+  if (smem > (size_t)smem_max) return 0;
+  const int nblk = (ny + R - 1) / R;
+  int cpt = (R * nx + tpb - 1) / tpb;                 // cells per thread: instantiated for 1, 2, 4, 8
+  if (cpt > lbm::RES_MAX_CPT) return 0;
+  cpt = cpt <= 1 ? 1 : cpt <= 2 ? 2 : cpt <= 4 ? 4 : 8;
+  int per_sm = 0;
+  if (resident_prepare(cpt, tpb, smem, &per_sm)) return 1;
+  if (nblk > per_sm * sms) return 0;
+  h->res_cpt = cpt;
+  h->resident = true;
+  h->res_rows = R;
+  h->res_tpb = tpb;
+  h->res_nblk = nblk;
+  h->res_chunk = std::max(2, env_int("LBM_RES_CHUNK", 1200));
+  const size_t words = (size_t)nblk * 2 * 2 * 3 * nx;
+  CK(cudaMalloc(&s.inbox, sizeof(unsigned long long) * words));
+  CK(cudaMemsetAsync(s.inbox, 0, sizeof(unsigned long long) * words, s.stream));
+  return 0;
+}
+
 // device objects of one slab.  obstacles: `rows_given` rows starting at lattice row `row_first`
 // (the whole grid in one-process mode, the slab's own rows in rank mode); flag rows whose lattice
 // row is not among them (ghost rows in rank mode) are left for the neighbours to push.
@@ -995,11 +1142,13 @@ int create_slab(lbm_lattice* h, Slab& s, const int* obstacles, int row_first, in
     if (e != cudaSuccess) return fail("cudaFuncSetAttribute(shared memory): %s", cudaGetErrorString(e));
   }
   s.np = std::max(s.nblk, s.tiles_x * s.tiles_y);
+  if (h->world == 1 && !h->comm && stream_steps(h) == 1 && decide_resident(h, s)) return 1;
+  if (h->resident) s.np = std::max(s.np, h->res_nblk);
   if (getenv("LBM_STREAM_TRACE") && s.tiles_x * s.tiles_y > 0) {
     CK(cudaMalloc(&s.trace, sizeof(unsigned long long) * 4 * (size_t)s.tiles_x * s.tiles_y));
     CK(cudaMemsetAsync(s.trace, 0, sizeof(unsigned long long) * 4 * (size_t)s.tiles_x * s.tiles_y, s.stream));
   }
-  CK(cudaMalloc(&s.partials, sizeof(double) * (size_t)h->chunk * s.np));
+  CK(cudaMalloc(&s.partials, sizeof(double) * (size_t)std::max(h->chunk, h->resident ? h->res_chunk : 0) * s.np));
   CK(cudaMalloc(&s.counter, sizeof(long long)));
   CK(cudaMemsetAsync(s.counter, 0, sizeof(long long), s.stream));
 
@@ -1070,8 +1219,12 @@ void set_config_string(lbm_lattice* h)
              c.s, c.nw, c.k0, c.minb, (int)h->stream_pdl, lbm::S_OUT_W, h->slabs[0].tile_h, h->slabs[0].tall_rows,
              lbm::S_OUT_W, h->slabs[0].tile_h2, h->slabs[0].tiles_y - h->slabs[0].tall_rows);
   }
+  if (h->resident)
+    snprintf(stream, sizeof stream, " resident=smem(rows/block=%d,tpb=%d,blocks=%d,smem=%zuKB,steps/launch=%d)",
+             h->res_rows, h->res_tpb, h->res_nblk, lbm::resident_smem_bytes(h->res_rows, h->p.nx, h->res_tpb) >> 10,
+             h->res_chunk);
   // graph replay and PDL apply to the one-step kernel on one GPU only
-  const bool one_step_only = S == 1 && !multi;
+  const bool one_step_only = S == 1 && !multi && !h->resident;
   snprintf(cfg, sizeof cfg, "vec=%d tpb=%d chunk=%d graph=%d pdl=%d fuse=%d%s slabs=%d halo=%s%s plane_stride=%lld",
            h->vec, h->tpb, h->chunk, (int)(h->use_graph && one_step_only), (int)(h->use_pdl && one_step_only),
            S, stream, h->world, mode, red, h->slabs[0].ps);
@@ -1340,6 +1493,7 @@ void lbm_destroy(lbm_lattice* h)
     if (s.counter) cudaFree(s.counter);
     if (s.macro) cudaFree(s.macro);
     if (s.trace) cudaFree(s.trace);
+    if (s.inbox) cudaFree(s.inbox);
     if (s.ev_begin) cudaEventDestroy(s.ev_begin);
     if (s.ev_end) cudaEventDestroy(s.ev_end);
     if (s.stream) cudaStreamDestroy(s.stream);

@@ -61,17 +61,23 @@ def test_single_steps_bit_exact(lbm, nx, ny):
             assert av_gpu == np.float32(av) or abs(float(av_gpu) - av) <= 1e-7 * abs(av)
 
 
+@pytest.mark.parametrize("resident", ["0", "1"])
 @pytest.mark.parametrize("nx,ny", SIZES)
-def test_run_bit_exact_and_av_vels(lbm, nx, ny, monkeypatch):
-    # a short chunk so that graph replay, the direct-launch tail and the un-accelerated last step
-    # are all exercised: 37 = 4 graph chunks of 8 + 5 direct
+def test_run_bit_exact_and_av_vels(lbm, nx, ny, resident, monkeypatch):
+    # resident=0: launches; a short chunk so that graph replay, the direct-launch tail and the
+    # un-accelerated last step are all exercised: 37 = 4 graph chunks of 8 + 5 direct.
+    # resident=1: the persistent kernel (the default for lattices this small), 7 steps per launch so
+    # that a run is several launches and the buffer parity flips between them: 37 = 5 x 7 + 2
     monkeypatch.setenv("LBM_CHUNK", "8")
+    monkeypatch.setenv("LBM_RESIDENT", resident)
+    monkeypatch.setenv("LBM_RES_CHUNK", "7")
     case = cases.random_case(nx, ny, seed=nx * 7 + ny, walls=(ny > 4))
     f0 = cases.perturbed_state(case, seed=ny)
     o = Oracle("f32b200", case)
     f = f0.copy()
     av = o.run(f, 37)
     with make(lbm, case) as lat:
+        assert ("resident=smem" in lat.config) == (resident == "1")
         lat.upload(f0)
         av_gpu = lat.run(37, f64=True)
         assert_state_bit_exact(lat.download(), f)
@@ -87,6 +93,7 @@ def test_run_bit_exact_and_av_vels(lbm, nx, ny, monkeypatch):
 def test_launch_variants_bit_exact(lbm, tpb, vec, monkeypatch):
     monkeypatch.setenv("LBM_TPB", str(tpb))
     monkeypatch.setenv("LBM_VEC", str(vec))
+    monkeypatch.setenv("LBM_RESIDENT", "0")     # the one-step launches, not the persistent kernel
     case = cases.random_case(192, 40, seed=5, walls=True)
     f0 = cases.perturbed_state(case, seed=5)
     o = Oracle("f32b200", case)
@@ -97,6 +104,79 @@ def test_launch_variants_bit_exact(lbm, tpb, vec, monkeypatch):
         lat.upload(f0)
         lat.run(20)
         assert_state_bit_exact(lat.download(), f)
+
+
+def _resident_fits(nx, ny, rows, tpb):
+    """mirror of decide_resident (lbm_engine.cu): shared memory of a block and cells per thread"""
+    r = min(max(rows, -(-ny // 148)), ny)
+    threads = min(min(512, max(32, tpb)), -(-r * nx // 32) * 32) // 32 * 32
+    smem = 8 * (9 * r + 6) * nx + 64 * threads
+    return smem <= 232448 and -(-r * nx // threads) <= 8, r
+
+
+@pytest.mark.parametrize("tpb,rows", [(512, 1), (64, 1), (128, 3), (256, 2), (512, 5), (96, 7), (512, 40), (32, 2)])
+@pytest.mark.parametrize("nx,ny", [(256, 96), (100, 31), (64, 20)])
+def test_persistent_kernel_shapes_bit_exact(lbm, tpb, rows, nx, ny, monkeypatch):
+    """lbm_resident_kernel: block shapes -- one row per block (every row is a boundary row), several
+    rows with an interior, a ragged last block, 1 / 2 / 4 / 8 cells per thread, the whole lattice in ONE
+    block (its own neighbour on both sides: 64 x 20 with 40 rows per block) -- one launch for the whole
+    run, then a second run from the canonical state"""
+    monkeypatch.setenv("LBM_RESIDENT", "1")
+    monkeypatch.setenv("LBM_RES_ROWS", str(rows))
+    monkeypatch.setenv("LBM_RES_TPB", str(tpb))
+    case = cases.random_case(nx, ny, seed=nx + 3 * ny + rows, walls=True)
+    f0 = cases.perturbed_state(case, seed=tpb)
+    o = Oracle("f32b200", case)
+    f = f0.copy()
+    av = o.run(f, 60)
+    fits, r = _resident_fits(nx, ny, rows, tpb)
+    with make(lbm, case) as lat:
+        if fits:
+            assert "resident=smem(rows/block=%d," % r in lat.config, lat.config
+        else:                              # too many rows for the shared memory of an SM, or > 8 cells per thread
+            assert "resident=" not in lat.config
+        lat.upload(f0)
+        av_gpu = lat.run(60, f64=True)
+        assert_state_bit_exact(lat.download(), f)
+        assert np.max(np.abs(av_gpu - av) / np.abs(av)) <= 1e-12
+        av2 = o.run(f, 3)
+        av_gpu2 = lat.run(3, f64=True)
+        assert_state_bit_exact(lat.download(), f)
+        assert np.max(np.abs(av_gpu2 - av2) / np.abs(av2)) <= 1e-12
+
+
+def test_persistent_kernel_is_the_default_for_the_small_shipped_cases(lbm):
+    for name, want in (("128x128", True), ("128x256", True), ("256x256", True), ("1024x1024", False)):   # 1024^2: too big for shared memory
+        with make(lbm, cases.shipped(name)) as lat:
+            assert ("resident=smem" in lat.config) == want, lat.config
+
+
+def test_persistent_kernel_equals_launches_on_a_long_run(lbm, monkeypatch):
+    """5000 steps of the shipped 256x256 case: the persistent kernel (5 launches) and the one-step
+    launches give the same bits -- thousands of neighbour handshakes without a single stale read"""
+    case = cases.shipped("256x256")
+    out = {}
+    for resident in ("1", "0"):
+        monkeypatch.setenv("LBM_RESIDENT", resident)
+        with make(lbm, case) as lat:
+            lat.init_equilibrium()
+            out[resident] = (lat.run(5000, f64=True), lat.download())
+    assert_state_bit_exact(out["1"][1], out["0"][1])
+    assert np.max(np.abs(out["1"][0] - out["0"][0]) / out["0"][0]) <= 1e-12
+
+
+def test_persistent_kernel_times_out_instead_of_hanging(lbm, monkeypatch):
+    """a block that never publishes its progress: its neighbours give up after ~1 s of SM clocks, the
+    launch ends, lbm_run reports the failure and the handle refuses further runs"""
+    monkeypatch.setenv("LBM_RESIDENT", "1")
+    monkeypatch.setenv("LBM_TEST_RESIDENT_STALL", "3")
+    case = cases.random_case(128, 64, seed=9, walls=True)
+    with make(lbm, case) as lat:
+        lat.init_equilibrium()
+        with pytest.raises(RuntimeError, match="timed out"):
+            lat.run(10)
+        with pytest.raises(RuntimeError, match="earlier run"):
+            lat.run(2)
 
 
 def test_device_init_equals_host_init(lbm):
