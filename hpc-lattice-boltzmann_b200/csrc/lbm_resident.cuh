@@ -7,7 +7,7 @@
 // Why: the shipped 128x128, 128x256 and 256x256 cases are 16 K - 64 K cells.  One timestep of them is
 // ~0.3 us of work for 148 SMs, but a launch chained to the previous one costs ~2.5 us even from a CUDA
 // graph with programmatic dependent launch (profiles/r1_tuning.md), so the one-step kernel ran those
-// cases at 7-25 % of the HBM roofline.  Measured on the way here (profiles/r2_tuning.md): a persistent
+// cases at 7-25 % of the HBM roofline.  Measured on the way here (profiles/r2_resident.md): a persistent
 // kernel that keeps the state in L2 and orders neighbouring blocks with st.release / ld.acquire flags
 // is no faster than launches (2.2-2.5 us per step: MEMBAR.ALL.GPU + flag + CCTL.IVALL round trips).
 //
