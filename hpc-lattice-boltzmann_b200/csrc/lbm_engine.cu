@@ -669,6 +669,8 @@ int launch_one_step(lbm_lattice* h, int cur, int fuse, int slot, long long step_
   return 0;
 }
 
+void set_config_string(lbm_lattice* h);
+
 // ---- the persistent small-lattice kernel (lbm_resident.cuh) ---------------------------------------
 // `n` timesteps from buffer `cur` into buffer cur^1 in one cooperative launch; partial sums of step i
 // go to slot i
@@ -722,12 +724,23 @@ int launch_resident(lbm_lattice* h, Slab& s, int cur, int n, int fuse_after)
   attr[0].val.cooperative = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  switch (h->res_cpt) {
-    case 1: CK(cudaLaunchKernelEx(&cfg, lbm::lbm_resident_kernel<1>, a)); break;
-    case 2: CK(cudaLaunchKernelEx(&cfg, lbm::lbm_resident_kernel<2>, a)); break;
-    case 4: CK(cudaLaunchKernelEx(&cfg, lbm::lbm_resident_kernel<4>, a)); break;
-    default: CK(cudaLaunchKernelEx(&cfg, lbm::lbm_resident_kernel<8>, a)); break;
+  cudaError_t e = env_int("LBM_TEST_RESIDENT_LAUNCH_FAIL", 0) ? cudaErrorCooperativeLaunchTooLarge : cudaSuccess;
+  if (e == cudaSuccess) {
+    switch (h->res_cpt) {
+      case 1: e = cudaLaunchKernelEx(&cfg, lbm::lbm_resident_kernel<1>, a); break;
+      case 2: e = cudaLaunchKernelEx(&cfg, lbm::lbm_resident_kernel<2>, a); break;
+      case 4: e = cudaLaunchKernelEx(&cfg, lbm::lbm_resident_kernel<4>, a); break;
+      default: e = cudaLaunchKernelEx(&cfg, lbm::lbm_resident_kernel<8>, a); break;
+    }
   }
+  if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorLaunchOutOfResources || e == cudaErrorNotSupported) {
+    // the device cannot hold the whole grid right now (e.g. an MPS partition smaller than the occupancy
+    // query assumed): nothing ran; the caller carries on with one launch per timestep
+    cudaGetLastError();
+    h->last_launches--;
+    return 2;
+  }
+  if (e != cudaSuccess) return fail("CUDA error launching the persistent kernel: %s", cudaGetErrorString(e));
   return 0;
 }
 
@@ -798,7 +811,13 @@ int run_steps(lbm_lattice* h, int iters, long long step0, bool last_segment)
     CK(cudaSetDevice(s.device));
     while (remaining > 0) {
       const int n = std::min(remaining, h->res_chunk);
-      if (launch_resident(h, s, cur, n, (remaining - n + more) > 0)) return 1;
+      const int rc = launch_resident(h, s, cur, n, (remaining - n + more) > 0);
+      if (rc == 2) {                  // not launchable here: this handle uses the one-step launches from now on
+        h->resident = false;
+        set_config_string(h);
+        break;
+      }
+      if (rc) return 1;
       if (reduce_chunk(h, n, false, h->res_nblk)) return 1;
       cur ^= 1;                       // a launch reads one buffer and leaves its result in the other
       remaining -= n;

@@ -165,6 +165,24 @@ def test_persistent_kernel_equals_launches_on_a_long_run(lbm, monkeypatch):
     assert np.max(np.abs(out["1"][0] - out["0"][0]) / out["0"][0]) <= 1e-12
 
 
+def test_persistent_kernel_falls_back_to_launches_when_it_cannot_be_placed(lbm, monkeypatch):
+    """a cooperative launch the device refuses (simulated: e.g. an MPS partition smaller than the
+    occupancy query assumed) is not an error: nothing ran, the handle carries on with one launch per step"""
+    monkeypatch.setenv("LBM_TEST_RESIDENT_LAUNCH_FAIL", "1")
+    case = cases.random_case(128, 64, seed=11, walls=True)
+    f0 = cases.perturbed_state(case, seed=11)
+    o = Oracle("f32b200", case)
+    f = f0.copy()
+    av = o.run(f, 30)
+    with make(lbm, case) as lat:
+        assert "resident=smem" in lat.config
+        lat.upload(f0)
+        av_gpu = lat.run(30, f64=True)
+        assert "resident=" not in lat.config
+        assert_state_bit_exact(lat.download(), f)
+        assert np.max(np.abs(av_gpu - av) / np.abs(av)) <= 1e-12
+
+
 def test_persistent_kernel_times_out_instead_of_hanging(lbm, monkeypatch):
     """a block that never publishes its progress: its neighbours give up after ~1 s of SM clocks, the
     launch ends, lbm_run reports the failure and the handle refuses further runs"""
