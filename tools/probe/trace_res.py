@@ -1,4 +1,7 @@
-"""tuning aid: per-phase clock64 trace of lbm_resident_kernel (needs tools/probe/liblbm_trace.so, built with -DLBM_RES_TRACE)"""
+"""tuning aid: per-phase clock64 trace of lbm_resident_kernel.  Needs a trace build of the library:
+  nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC,-fopenmp -DLBM_RES_TRACE \
+       -shared hpc-lattice-boltzmann_b200/csrc/lbm_engine.cu -o tools/probe/liblbm_trace.so -lcudart
+  python tools/probe/trace_res.py 128x128 out.txt"""
 import importlib, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
