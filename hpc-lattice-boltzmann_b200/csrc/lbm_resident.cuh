@@ -22,8 +22,10 @@
 // can only be one step ahead of its neighbour, because it needs the neighbour's halo of step s to
 // compute step s+1.  Boundary rows are relaxed and sent first, interior rows next, the poll last.
 //
-// Critical path of a step: relax the boundary rows -> 64-bit store -> L2 -> neighbour's poll -> bar.sync.
-// Spins are bounded (~1 s of SM clocks) and raise *timed_out instead of hanging the GPU.
+// Critical path of a step: relax the boundary rows -> 64-bit store -> L2 (~850 cycles until the neighbour's
+// poll sees it, whatever the access flavour: tools/probe/probe_pingpong.cu) -> bar.sync.  Measured on B200:
+// 128x128 2.78 -> 1.26 us per step, 128x256 2.78 -> 1.26, 256x256 2.84 -> 1.60 (profiles/r2_resident.md).
+// Spins are bounded (2^22 polls, ~1 s) and raise *timed_out instead of hanging the GPU.
 #pragma once
 #include "lbm_kernels.cuh"
 
