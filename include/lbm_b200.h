@@ -78,7 +78,10 @@ int lbm_download(lbm_lattice* h, float* const cells[9]);
 int lbm_step(lbm_lattice* h, float* av_vel);
 
 /* the whole `for tt` loop (d2q9-bgk.c:206-234): iters timesteps with no host involvement,
- * av_vels[0..iters) written at the end.  av_vels may be NULL. */
+ * av_vels[0..iters) written at the end.  av_vels may be NULL.  How the loop is mapped onto the GPU is
+ * decided at lbm_create from the lattice alone (lbm_config_string tells): one persistent launch for
+ * lattices that fit the SMs' shared memory, two timesteps per launch for slabs that stream from HBM, one
+ * launch per timestep otherwise -- the results are bit-identical whichever runs. */
 int lbm_run(lbm_lattice* h, int iters, float* av_vels);
 int lbm_run_f64(lbm_lattice* h, int iters, double* av_vels);   /* same, un-narrowed averages */
 
